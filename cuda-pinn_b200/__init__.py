@@ -1,0 +1,303 @@
+"""cuda-pinn_b200 — host-side mirror of the reference's intended `network` interface over the C ABI.
+
+The product is the CUDA library (csrc/ → libpinn_b200.so, entry points in include/pinn_abi.h) and
+the C++ `network<T>` header (include/network.cuh).  This module is the thin ctypes binding the
+tests and bench.py drive it through; it contains no arithmetic and has NO fallback: if the
+shared library is missing or there is no B200, construction raises.
+
+(The directory name has a hyphen, so import it with importlib — see `load()` in
+`__graft_entry__.py`, which registers it as `cuda_pinn_b200`.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpinn_b200.so")
+
+PDE_BURGERS, PDE_HELMHOLTZ, PDE_ALLEN_CAHN, PDE_NAVIER_STOKES, PDE_HEAT = 0, 1, 2, 3, 4
+SET_INTERIOR, SET_BOUNDARY, SET_INITIAL = 0, 1, 2
+PREC_FP32, PREC_TF32X3, PREC_BF16 = 0, 1, 2
+ABI_VERSION = 1
+
+
+class PinnConfig(C.Structure):
+    """`pinn_config` of include/pinn_abi.h."""
+    _fields_ = [
+        ("abi_version", C.c_int32), ("pde", C.c_int32), ("d_in", C.c_int32), ("d_out", C.c_int32),
+        ("width", C.c_int32), ("depth", C.c_int32), ("precision", C.c_int32), ("device", C.c_int32),
+        ("rank", C.c_int32), ("nranks", C.c_int32),
+        ("n_interior", C.c_uint64), ("n_boundary", C.c_uint64), ("n_initial", C.c_uint64),
+        ("seed_interior", C.c_uint64), ("seed_boundary", C.c_uint64), ("seed_initial", C.c_uint64),
+        ("seed_weights", C.c_uint64),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("lambda_r", C.c_float), ("lambda_b", C.c_float), ("lambda_0", C.c_float),
+        ("pde_param", C.c_float),
+    ]
+
+
+class PinnStepOut(C.Structure):
+    _fields_ = [("loss", C.c_float), ("mse_residual", C.c_float), ("mse_boundary", C.c_float),
+                ("mse_initial", C.c_float), ("step", C.c_uint64)]
+
+
+class PinnProfile(C.Structure):
+    _fields_ = [("launches", C.c_uint64), ("step_kernel_ms", C.c_double), ("step_kernel_count", C.c_uint64),
+                ("grid", C.c_int32), ("block", C.c_int32), ("smem_bytes", C.c_int32), ("kernel_id", C.c_int32)]
+
+
+# every symbol include/pinn_abi.h declares (tests check the library exports exactly these)
+ABI_SYMBOLS = [
+    "pinn_config_default", "pinn_num_channels", "pinn_num_params", "pinn_shard_range",
+    "pinn_create", "pinn_destroy", "pinn_last_error",
+    "pinn_set_params", "pinn_get_params", "pinn_get_grads", "pinn_get_optimizer", "pinn_set_optimizer",
+    "pinn_sample_points", "pinn_resample_points", "pinn_set_points", "pinn_get_points", "pinn_local_count",
+    "pinn_train_step", "pinn_train_step_host", "pinn_train_steps", "pinn_loss_grad",
+    "pinn_forward", "pinn_residual", "pinn_synchronize",
+    "pinn_comm_unique_id", "pinn_comm_init", "pinn_step_local", "pinn_step_apply",
+    "pinn_grad_buffer", "pinn_stream", "pinn_profile_enable", "pinn_profile_get",
+]
+
+_lib = None
+
+
+class PinnError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"[pinn status {code}] {message}")
+        self.code = code
+
+
+def lib():
+    """Load libpinn_b200.so; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python __graft_entry__.py build` (nvcc, sm_100a). "
+                          "There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    vp, cfgp = C.c_void_p, P(PinnConfig)
+    L.pinn_config_default.argtypes = [cfgp, C.c_int]
+    L.pinn_num_channels.argtypes = [cfgp]
+    L.pinn_num_params.argtypes = [cfgp]; L.pinn_num_params.restype = C.c_size_t
+    L.pinn_shard_range.argtypes = [C.c_uint64, C.c_int32, C.c_int32, P(C.c_uint64), P(C.c_uint64)]
+    L.pinn_shard_range.restype = None
+    L.pinn_create.argtypes = [P(vp), cfgp]
+    L.pinn_destroy.argtypes = [vp]; L.pinn_destroy.restype = None
+    L.pinn_last_error.argtypes = [vp]; L.pinn_last_error.restype = C.c_char_p
+    L.pinn_set_params.argtypes = [vp, vp, C.c_size_t, C.c_int]
+    L.pinn_get_params.argtypes = [vp, vp, C.c_size_t]
+    L.pinn_get_grads.argtypes = [vp, vp, C.c_size_t]
+    L.pinn_get_optimizer.argtypes = [vp, vp, vp, C.c_size_t, P(C.c_uint64)]
+    L.pinn_set_optimizer.argtypes = [vp, vp, vp, C.c_size_t, C.c_uint64]
+    L.pinn_sample_points.argtypes = [vp]
+    L.pinn_resample_points.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64]
+    L.pinn_set_points.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.pinn_get_points.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.pinn_local_count.argtypes = [vp, C.c_int]; L.pinn_local_count.restype = C.c_size_t
+    L.pinn_train_step.argtypes = [vp, P(PinnStepOut)]
+    L.pinn_train_step_host.argtypes = [vp, vp, C.c_size_t, P(PinnStepOut)]
+    L.pinn_train_steps.argtypes = [vp, C.c_int, P(PinnStepOut)]
+    L.pinn_loss_grad.argtypes = [vp, P(PinnStepOut)]
+    L.pinn_forward.argtypes = [vp, vp, vp, C.c_size_t]
+    L.pinn_residual.argtypes = [vp, vp, vp, vp, C.c_size_t]
+    L.pinn_synchronize.argtypes = [vp]
+    L.pinn_comm_unique_id.argtypes = [vp]
+    L.pinn_comm_init.argtypes = [vp, vp]
+    L.pinn_step_local.argtypes = [vp]
+    L.pinn_step_apply.argtypes = [vp, P(PinnStepOut)]
+    L.pinn_grad_buffer.argtypes = [vp, P(C.c_size_t)]; L.pinn_grad_buffer.restype = vp
+    L.pinn_stream.argtypes = [vp]; L.pinn_stream.restype = vp
+    L.pinn_profile_enable.argtypes = [vp, C.c_int]
+    L.pinn_profile_get.argtypes = [vp, P(PinnProfile), C.c_int]
+    _lib = L
+    return L
+
+
+def default_config(which, **overrides):
+    """BASELINE config C1..C5 (pinn_config_default) with field overrides."""
+    cfg = PinnConfig()
+    rc = lib().pinn_config_default(C.byref(cfg), which)
+    if rc:
+        raise PinnError(rc, "pinn_config_default: invalid config index")
+    for k, v in overrides.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def shard_range(n, rank, nranks):
+    b, e = C.c_uint64(), C.c_uint64()
+    lib().pinn_shard_range(n, rank, nranks, C.byref(b), C.byref(e))
+    return int(b.value), int(e.value)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Network:
+    """Handle on one GPU's PINN (mirrors the `network` class of include/network.cuh)."""
+
+    def __init__(self, cfg):
+        self._L = lib()
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        rc = self._L.pinn_create(C.byref(self._h), C.byref(cfg))
+        if rc:
+            raise PinnError(rc, self._L.pinn_last_error(None).decode())
+        self.num_params = int(self._L.pinn_num_params(C.byref(cfg)))
+        self.num_channels = int(self._L.pinn_num_channels(C.byref(cfg)))
+        self.n_res = 3 if cfg.pde == PDE_NAVIER_STOKES else 1
+
+    # -- lifetime
+    def close(self):
+        if self._h:
+            self._L.pinn_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise PinnError(rc, self._L.pinn_last_error(self._h).decode())
+
+    # -- parameters
+    def get_params(self):
+        w = np.empty(self.num_params, dtype=np.float32)
+        self._check(self._L.pinn_get_params(self._h, _ptr(w), w.size))
+        return w
+
+    def set_params(self, w, reset_optimizer=True):
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        self._check(self._L.pinn_set_params(self._h, _ptr(w), w.size, int(reset_optimizer)))
+
+    def get_grads(self):
+        g = np.empty(self.num_params, dtype=np.float32)
+        self._check(self._L.pinn_get_grads(self._h, _ptr(g), g.size))
+        return g
+
+    def get_optimizer(self):
+        m = np.empty(self.num_params, dtype=np.float32)
+        v = np.empty(self.num_params, dtype=np.float32)
+        t = C.c_uint64()
+        self._check(self._L.pinn_get_optimizer(self._h, _ptr(m), _ptr(v), m.size, C.byref(t)))
+        return m, v, int(t.value)
+
+    def set_optimizer(self, m, v, step):
+        m = np.ascontiguousarray(m, dtype=np.float32); v = np.ascontiguousarray(v, dtype=np.float32)
+        self._check(self._L.pinn_set_optimizer(self._h, _ptr(m), _ptr(v), m.size, step))
+
+    # -- points
+    def sample_points(self):
+        self._check(self._L.pinn_sample_points(self._h))
+
+    def resample_points(self, si, sb, s0):
+        self._check(self._L.pinn_resample_points(self._h, si, sb, s0))
+
+    def local_count(self, which):
+        return int(self._L.pinn_local_count(self._h, which))
+
+    def get_points(self, which):
+        n = self.local_count(which)
+        x = np.empty((n, self.cfg.d_in), dtype=np.float32)
+        self._check(self._L.pinn_get_points(self._h, which, _ptr(x), n))
+        return x
+
+    def set_points(self, which, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        self._check(self._L.pinn_set_points(self._h, which, _ptr(x), len(x)))
+
+    # -- hot path
+    @staticmethod
+    def _out(o):
+        return dict(loss=o.loss, mse_residual=o.mse_residual, mse_boundary=o.mse_boundary,
+                    mse_initial=o.mse_initial, step=int(o.step))
+
+    def train_step(self, read_loss=True):
+        o = PinnStepOut()
+        self._check(self._L.pinn_train_step(self._h, C.byref(o) if read_loss else None))
+        return self._out(o) if read_loss else None
+
+    def train_step_host(self, x_ptr, n):
+        """x_ptr: integer address (or numpy array) of HOST points [n, d_in] float32."""
+        o = PinnStepOut()
+        p = _ptr(x_ptr) if isinstance(x_ptr, np.ndarray) else C.c_void_p(x_ptr)
+        self._check(self._L.pinn_train_step_host(self._h, p, n, C.byref(o)))
+        return self._out(o)
+
+    def train_steps(self, k, read_loss=True):
+        o = PinnStepOut()
+        self._check(self._L.pinn_train_steps(self._h, k, C.byref(o) if read_loss else None))
+        return self._out(o) if read_loss else None
+
+    def loss_grad(self):
+        o = PinnStepOut()
+        self._check(self._L.pinn_loss_grad(self._h, C.byref(o)))
+        return self._out(o)
+
+    def step_local(self):
+        self._check(self._L.pinn_step_local(self._h))
+
+    def step_apply(self, read_loss=True):
+        o = PinnStepOut()
+        self._check(self._L.pinn_step_apply(self._h, C.byref(o) if read_loss else None))
+        return self._out(o) if read_loss else None
+
+    def forward(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.empty((len(x), self.cfg.d_out), dtype=np.float32)
+        self._check(self._L.pinn_forward(self._h, _ptr(x), _ptr(y), len(x)))
+        return y
+
+    def residual(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.empty((len(x), self.cfg.d_out, self.num_channels), dtype=np.float32)
+        r = np.empty((len(x), self.n_res), dtype=np.float32)
+        self._check(self._L.pinn_residual(self._h, _ptr(x), _ptr(y), _ptr(r), len(x)))
+        return y, r
+
+    def synchronize(self):
+        self._check(self._L.pinn_synchronize(self._h))
+
+    # -- multi-GPU
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_char * 128)()
+        rc = lib().pinn_comm_unique_id(buf)
+        if rc:
+            raise PinnError(rc, lib().pinn_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, id_bytes):
+        buf = (C.c_char * 128).from_buffer_copy(id_bytes)
+        self._check(self._L.pinn_comm_init(self._h, buf))
+
+    def grad_buffer(self):
+        n = C.c_size_t()
+        p = self._L.pinn_grad_buffer(self._h, C.byref(n))
+        return int(p), int(n.value)
+
+    def stream(self):
+        return int(self._L.pinn_stream(self._h) or 0)
+
+    # -- measurement
+    def profile_enable(self, on=True):
+        self._check(self._L.pinn_profile_enable(self._h, int(on)))
+
+    def profile_get(self, reset=False):
+        p = PinnProfile()
+        self._check(self._L.pinn_profile_get(self._h, C.byref(p), int(reset)))
+        return dict(launches=int(p.launches), step_kernel_ms=p.step_kernel_ms, step_kernel_count=int(p.step_kernel_count),
+                    grid=p.grid, block=p.block, smem_bytes=p.smem_bytes, kernel_id=p.kernel_id)

@@ -1,0 +1,755 @@
+// pinn_capi.cu — host side of the B200 PINN train step behind the C ABI of include/pinn_abi.h.
+// Owns device memory, the stream, kernel selection and (N>1) the NCCL communicator.
+// There is no CPU arithmetic path here: every entry point either runs CUDA kernels or fails.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../../include/pinn_abi.h"
+#include "pinn_device.cuh"
+#include "pinn_fused_fp32.cuh"
+
+using namespace pinn;
+
+// ------------------------------------------------------------------------------------------
+// small kernels around the fused step
+// ------------------------------------------------------------------------------------------
+
+// Collocation generation (reference src/utils.cu is empty): one thread per point of the shard.
+__global__ void sample_points_kernel(const NetDims nd, int set, uint64_t seed, uint64_t begin, uint64_t count,
+                                     float* __restrict__ x) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float p[3];
+    sample_point(nd, set, seed, begin + i, p);
+    for (int k = 0; k < nd.d_in; k++) x[i * nd.d_in + k] = p[k];
+}
+
+// gbuf[i] = sum over CTA partial rows in fixed order; rows are zeroed for the next step.
+__global__ void reduce_partials_kernel(float* __restrict__ partial, int nrows, int PP, int n_out,
+                                       float* __restrict__ gbuf, unsigned long long* step, int bump) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && bump) *step += 1ULL;
+    if (i >= n_out) return;
+    float s = 0.0f;
+    for (int r = 0; r < nrows; r++) {
+        const size_t idx = (size_t)r * PP + i;
+        s += partial[idx];
+        partial[idx] = 0.0f;
+    }
+    gbuf[i] = s;
+}
+
+struct AdamArgs {
+    float lr, beta1, beta2, eps;
+    float lambda_r, lambda_b, lambda_0;
+    double inv_nf, inv_nb, inv_n0;
+};
+
+// Adam on the flat parameter vector + refresh of the transposed copy.
+__global__ void adam_kernel(const NetDims nd, const AdamArgs a, float* __restrict__ params,
+                            float* __restrict__ paramsT, float* __restrict__ m, float* __restrict__ v,
+                            const float* __restrict__ gbuf, const unsigned long long* __restrict__ step,
+                            float* __restrict__ loss_out, int* __restrict__ flag, int apply) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        const float mr = (float)((double)gbuf[nd.P + 0] * a.inv_nf);
+        const float mb = (float)((double)gbuf[nd.P + 1] * a.inv_nb);
+        const float m0 = (float)((double)gbuf[nd.P + 2] * a.inv_n0);
+        const float loss = a.lambda_r * mr + a.lambda_b * mb + a.lambda_0 * m0;
+        loss_out[0] = loss; loss_out[1] = mr; loss_out[2] = mb; loss_out[3] = m0;
+        if (!isfinite(loss)) *flag = PINN_ERR_DEVICE_OVERFLOW;   // reference runtime.cuh error channel
+    }
+    if (i >= nd.P || !apply) return;
+    const double t = (double)(*step);
+    const float c1 = (float)(1.0 / (1.0 - pow((double)a.beta1, t)));
+    const float c2 = (float)(1.0 / (1.0 - pow((double)a.beta2, t)));
+    const float g = gbuf[i];
+    const float mi = a.beta1 * m[i] + (1.0f - a.beta1) * g;
+    const float vi = a.beta2 * v[i] + (1.0f - a.beta2) * (g * g);
+    m[i] = mi; v[i] = vi;
+    const float mh = mi * c1, vh = vi * c2;
+    const float w = params[i] - a.lr * (mh / (sqrtf(vh) + a.eps));
+    params[i] = w;
+    // transposed mirror W^T[l] ([fan_out, fan_in]) used by the dA contraction
+    int l = 1;
+    while (l <= nd.L && i >= nd.offW[l + 1]) l++;
+    const int fi = nd.fan_in(l), fo = nd.fan_out(l);
+    if (i < nd.offB[l]) {
+        const int r = i - nd.offW[l], k = r / fo, j = r - k * fo;
+        paramsT[nd.offW[l] + j * fi + k] = w;
+    } else {
+        paramsT[i] = w;
+    }
+}
+
+__global__ void transpose_params_kernel(const NetDims nd, const float* __restrict__ params,
+                                        float* __restrict__ paramsT) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nd.P) return;
+    int l = 1;
+    while (l <= nd.L && i >= nd.offW[l + 1]) l++;
+    const int fi = nd.fan_in(l), fo = nd.fan_out(l);
+    if (i < nd.offB[l]) {
+        const int r = i - nd.offW[l], k = r / fo, j = r - k * fo;
+        paramsT[nd.offW[l] + j * fi + k] = params[i];
+    } else {
+        paramsT[i] = params[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen (torch's bundled libnccl.so.2 when loaded in a torch process, else the
+// system one); no link-time dependency so single-GPU users need no NCCL at all.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct NcclId { char b[128]; };          // ncclUniqueId (nccl.h: 128 opaque bytes, passed by value)
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+bool nccl_load(std::string& err) {
+    if (g_nccl.ok) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+    auto sym = [&](const char* s) { return dlsym(g_nccl.handle, s); };
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+        err = "libnccl is missing a required symbol"; return false;
+    }
+    g_nccl.ok = true;
+    return true;
+}
+constexpr int kNcclFloat32 = 7, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+std::string g_create_error;
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+typedef void (*fused_fn)(const NetDims, const FusedArgs);
+
+struct pinn_ctx {
+    pinn_config cfg{};
+    NetDims nd{};
+    cudaStream_t stream = nullptr;
+    float *d_params = nullptr, *d_paramsT = nullptr, *d_m = nullptr, *d_v = nullptr;
+    float *d_gbuf = nullptr, *d_partial = nullptr, *d_stash = nullptr, *d_loss = nullptr;
+    unsigned long long* d_step = nullptr;
+    int* d_flag = nullptr;
+    float* d_x[3] = {nullptr, nullptr, nullptr};
+    uint64_t begin[3] = {0, 0, 0}, cap[3] = {0, 0, 0}, n_local[3] = {0, 0, 0};
+    uint64_t seeds[3] = {0, 0, 0};
+    float scale[3] = {0, 0, 0};
+    float* h_pinned = nullptr;          // [8]: loss record + flag
+    // launch configuration of the fused kernels
+    fused_fn kern_full = nullptr, kern_val = nullptr;
+    int TP = 32, UT = 4, threads = 0, smem_full = 0, smem_val = 0, grid_cap_full = 0, grid_cap_val = 0;
+    int nrows_cta = 0, nslot = 1, kernel_id = 0, num_sms = 148;
+    long long stash_per_cta = 0;
+    AdamArgs adam{};
+    void* comm = nullptr;
+    std::string err;
+    // profiling
+    bool prof = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    double kernel_ms = 0.0; uint64_t kernel_count = 0, launches = 0;
+    int last_grid = 0;
+    uint64_t host_step = 0;
+};
+
+static int fail(pinn_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CUDA_TRY(c, fn, call)                                                                         \
+    do { cudaError_t e_ = (call);                                                                     \
+         if (e_ != cudaSuccess) return fail((c), PINN_ERR_CUDA, std::string(fn) + ": " + #call + " -> " + \
+                                            cudaGetErrorString(e_)); } while (0)
+
+static int pde_shape(int pde, int* n_space, int* n2, int* n_res, int* d_out) {
+    switch (pde) {
+    case PINN_PDE_BURGERS:       *n_space = 1; *n2 = 1; *n_res = 1; *d_out = 1; return 1;
+    case PINN_PDE_HELMHOLTZ:     *n_space = 2; *n2 = 2; *n_res = 1; *d_out = 1; return 1;
+    case PINN_PDE_ALLEN_CAHN:    *n_space = 2; *n2 = 2; *n_res = 1; *d_out = 1; return 1;
+    case PINN_PDE_HEAT:          *n_space = 2; *n2 = 2; *n_res = 1; *d_out = 1; return 1;
+    case PINN_PDE_NAVIER_STOKES: *n_space = 2; *n2 = 2; *n_res = 3; *d_out = 3; return 1;
+    }
+    return 0;
+}
+
+static bool make_dims(const pinn_config* cfg, NetDims* nd, std::string& why) {
+    memset(nd, 0, sizeof(*nd));
+    int n_space, n2, n_res, d_out;
+    if (!pde_shape(cfg->pde, &n_space, &n2, &n_res, &d_out)) { why = "unknown pde"; return false; }
+    const int want_din = n_space + (cfg->pde == PINN_PDE_HELMHOLTZ ? 0 : 1);
+    if (cfg->d_in != want_din) { why = "d_in does not match the pde"; return false; }
+    if (cfg->d_out != d_out) { why = "d_out does not match the pde"; return false; }
+    if (cfg->depth < 1 || cfg->depth > kMaxLayers) { why = "depth out of range [1,32]"; return false; }
+    if (cfg->width < 4 || cfg->width > 1024 || (cfg->width & 3)) { why = "width must be a multiple of 4 in [4,1024]"; return false; }
+    nd->d_in = cfg->d_in; nd->d_out = cfg->d_out; nd->H = cfg->width; nd->L = cfg->depth; nd->pde = cfg->pde;
+    nd->n2 = n2; nd->n_space = n_space; nd->n_res = n_res; nd->has_t = cfg->d_in > n_space;
+    nd->C = 1 + cfg->d_in + n2;
+    for (int k = 0; k < cfg->d_in; k++) {
+        const bool is_t = nd->has_t && k == cfg->d_in - 1;
+        if (is_t) { nd->lo[k] = 0.0f; nd->hi[k] = 1.0f; }
+        else if (cfg->pde == PINN_PDE_NAVIER_STOKES) { nd->lo[k] = 0.0f; nd->hi[k] = kTwoPi; }
+        else { nd->lo[k] = -1.0f; nd->hi[k] = 1.0f; }
+        nd->span[k] = nd->hi[k] - nd->lo[k];
+    }
+    size_t off = 0;
+    for (int l = 1; l <= nd->L + 1; l++) {
+        nd->offW[l] = (int)off; off += (size_t)nd->fan_in(l) * nd->fan_out(l);
+        nd->offB[l] = (int)off; off += (size_t)nd->fan_out(l);
+    }
+    nd->P = (int)off;
+    nd->PP = (int)((off + 3 + 31) & ~(size_t)31);
+    const float k = cfg->pde_param != 0.0f ? cfg->pde_param : 1.0f;
+    nd->k2 = k * k;
+    return true;
+}
+
+extern "C" {
+
+int pinn_config_default(pinn_config* cfg, int which) {
+    if (!cfg || which < 1 || which > 5) return PINN_ERR_INVALID_ARGUMENT;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->abi_version = PINN_ABI_VERSION;
+    static const int pde[6] = {0, PINN_PDE_BURGERS, PINN_PDE_BURGERS, PINN_PDE_HELMHOLTZ, PINN_PDE_ALLEN_CAHN, PINN_PDE_NAVIER_STOKES};
+    static const int din[6] = {0, 2, 2, 2, 3, 3}, dout[6] = {0, 1, 1, 1, 1, 3};
+    static const int width[6] = {0, 20, 20, 64, 128, 256}, depth[6] = {0, 8, 8, 4, 6, 8};
+    static const uint64_t nf[6] = {0, 4096, 25600, 1ull << 20, 1ull << 24, 1ull << 26};
+    cfg->pde = pde[which]; cfg->d_in = din[which]; cfg->d_out = dout[which];
+    cfg->width = width[which]; cfg->depth = depth[which];
+    cfg->precision = PINN_PREC_FP32; cfg->device = 0; cfg->rank = 0; cfg->nranks = 1;
+    cfg->n_interior = nf[which];
+    const uint64_t nb = nf[which] / 32 > 256 ? nf[which] / 32 : 256;
+    cfg->n_boundary = nb;
+    cfg->n_initial = (cfg->pde == PINN_PDE_HELMHOLTZ) ? 0 : nb;
+    cfg->seed_interior = 0x5EED0001ull; cfg->seed_boundary = 0x5EED0002ull; cfg->seed_initial = 0x5EED0003ull;
+    cfg->seed_weights = 0x5EED0100ull;
+    cfg->lr = 1e-3f; cfg->beta1 = 0.9f; cfg->beta2 = 0.999f; cfg->eps = 1e-8f;
+    cfg->lambda_r = cfg->lambda_b = cfg->lambda_0 = 1.0f;
+    cfg->pde_param = 0.0f;
+    return PINN_OK;
+}
+
+int pinn_num_channels(const pinn_config* cfg) {
+    NetDims nd; std::string why;
+    if (!cfg || !make_dims(cfg, &nd, why)) return -1;
+    return nd.C;
+}
+
+size_t pinn_num_params(const pinn_config* cfg) {
+    NetDims nd; std::string why;
+    if (!cfg || !make_dims(cfg, &nd, why)) return 0;
+    return (size_t)nd.P;
+}
+
+void pinn_shard_range(uint64_t n, int32_t rank, int32_t nranks, uint64_t* begin, uint64_t* end) {
+    *begin = (uint64_t)(((unsigned __int128)n * (unsigned)rank) / (unsigned)nranks);
+    *end = (uint64_t)(((unsigned __int128)n * (unsigned)(rank + 1)) / (unsigned)nranks);
+}
+
+const char* pinn_last_error(const pinn_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+}  // extern "C"
+
+// ---- kernel selection -------------------------------------------------------------------
+template <int DIN, int N2, bool FULL>
+static fused_fn pick_ut_tp(int UT, int TP) {
+    if (UT == 4 && TP == 32) return fused_step_fp32<DIN, N2, FULL, 4, 32>;
+    if (UT == 8 && TP == 32) return fused_step_fp32<DIN, N2, FULL, 8, 32>;
+    if (UT == 8 && TP == 16) return fused_step_fp32<DIN, N2, FULL, 8, 16>;
+    return nullptr;
+}
+static fused_fn pick_kernel(int d_in, int n2, bool full, int UT, int TP) {
+    if (full) {
+        if (d_in == 2 && n2 == 1) return pick_ut_tp<2, 1, true>(UT, TP);
+        if (d_in == 2 && n2 == 2) return pick_ut_tp<2, 2, true>(UT, TP);
+        if (d_in == 3 && n2 == 2) return pick_ut_tp<3, 2, true>(UT, TP);
+    } else {
+        if (d_in == 2) return pick_ut_tp<2, 0, false>(UT, TP);
+        if (d_in == 3) return pick_ut_tp<3, 0, false>(UT, TP);
+    }
+    return nullptr;
+}
+
+static int configure_kernels(pinn_ctx* c) {
+    const NetDims& nd = c->nd;
+    cudaDeviceProp prop;
+    CUDA_TRY(c, "pinn_create", cudaGetDeviceProperties(&prop, c->cfg.device));
+    c->num_sms = prop.multiProcessorCount;
+    const int max_smem = (int)prop.sharedMemPerBlockOptin;
+    const int H = nd.H, rows = (H + 3) & ~3;
+    c->UT = (H % 8 == 0 && H >= 32) ? 8 : 4;
+    auto smem_for = [&](int nc, int tp) { return (int)(2 * (size_t)rows * (nc * tp + 4) * sizeof(float)); };
+    c->TP = 32;
+    if (smem_for(nd.C, 32) > max_smem || 32 * (H / c->UT) > 512) {
+        c->TP = 16;
+        if (c->UT != 8) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: width needs the 16-point tile, which requires width % 8 == 0");
+        if (smem_for(nd.C, 16) > max_smem || 16 * (H / c->UT) > 512)
+            return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: width too large for the FP32 fused kernel");
+    }
+    c->threads = c->TP * (H / c->UT);
+    c->smem_full = smem_for(nd.C, c->TP);
+    c->smem_val = smem_for(1, c->TP);
+    c->kern_full = pick_kernel(nd.d_in, nd.n2, true, c->UT, c->TP);
+    c->kern_val = pick_kernel(nd.d_in, nd.n2, false, c->UT, c->TP);
+    if (!c->kern_full || !c->kern_val) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: no kernel for this configuration");
+    CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_full, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_full));
+    CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_val, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_val));
+    int occ_f = 0, occ_v = 0;
+    CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, c->kern_full, c->threads, c->smem_full));
+    CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_v, c->kern_val, c->threads, c->smem_val));
+    if (occ_f < 1 || occ_v < 1) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: fused kernel does not fit on an SM");
+    if (occ_v > 8) occ_v = 8;
+    c->grid_cap_full = occ_f * c->num_sms;
+    c->grid_cap_val = occ_v * c->num_sms;
+    const int ntiles_hidden = (H / 4) * (H / 4);
+    int nslot = c->threads / ntiles_hidden;
+    c->nslot = nslot < 1 ? 1 : (nslot > 8 ? 8 : nslot);
+    c->kernel_id = (c->UT == 8 ? 10 : 0) + (c->TP == 16 ? 1 : 0);
+    return PINN_OK;
+}
+
+static int tiles_of(uint64_t n, int tp) { return (int)((n + tp - 1) / tp); }
+
+static void host_init_params(const NetDims& nd, uint64_t seed, std::vector<float>& w) {
+    w.assign(nd.P, 0.0f);
+    for (int l = 1; l <= nd.L + 1; l++) {
+        const int fi = nd.fan_in(l), fo = nd.fan_out(l);
+        const float a = (float)std::sqrt(6.0 / (double)(fi + fo));
+        const float two_a = 2.0f * a;
+        for (size_t k = 0; k < (size_t)fi * fo; k++) w[nd.offW[l] + k] = fmaf(two_a, u01(seed + (uint64_t)l, k), -a);
+    }
+}
+
+static int launch_fused(pinn_ctx* c, bool full, const PointSet* sets, int nsets, int mode, float* y_out, float* r_out) {
+    int total = 0;
+    for (int i = 0; i < nsets; i++) total += sets[i].ntiles;
+    if (total == 0) return PINN_OK;
+    FusedArgs a{};
+    a.params = c->d_params; a.paramsT = c->d_paramsT;
+    a.nsets = nsets;
+    for (int i = 0; i < nsets; i++) a.sets[i] = sets[i];
+    a.partial = c->d_partial; a.stash = c->d_stash; a.nslot = c->nslot; a.stash_per_cta = c->stash_per_cta;
+    a.mode = mode; a.y_out = y_out; a.r_out = r_out;
+    const int cap = full ? c->grid_cap_full : c->grid_cap_val;
+    const int grid = total < cap ? total : cap;
+    const bool timed = c->prof && full && mode == 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timed) {
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, c->stream);
+    }
+    (full ? c->kern_full : c->kern_val)<<<grid, c->threads, full ? c->smem_full : c->smem_val, c->stream>>>(c->nd, a);
+    if (timed) { cudaEventRecord(e1, c->stream); c->pending.emplace_back(e0, e1); }
+    if (full) c->last_grid = grid;
+    c->launches++;
+    CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
+    return PINN_OK;
+}
+
+static int run_local(pinn_ctx* c, int bump_step) {
+    PointSet s{};
+    s.x = c->d_x[0]; s.n = c->n_local[0]; s.scale = c->scale[0]; s.set = PINN_SET_INTERIOR; s.ntiles = tiles_of(s.n, c->TP);
+    int rc = launch_fused(c, true, &s, 1, 0, nullptr, nullptr);
+    if (rc) return rc;
+    PointSet v[2]; int nv = 0;
+    for (int k = 1; k <= 2; k++) {
+        if (c->n_local[k] == 0) continue;
+        v[nv].x = c->d_x[k]; v[nv].n = c->n_local[k]; v[nv].scale = c->scale[k]; v[nv].set = k;
+        v[nv].ntiles = tiles_of(c->n_local[k], c->TP); nv++;
+    }
+    if (nv) { rc = launch_fused(c, false, v, nv, 0, nullptr, nullptr); if (rc) return rc; }
+    const int n_out = c->nd.P + 3;
+    reduce_partials_kernel<<<(n_out + 255) / 256, 256, 0, c->stream>>>(c->d_partial, c->nrows_cta * c->nslot, c->nd.PP,
+                                                                     n_out, c->d_gbuf, c->d_step, bump_step);
+    c->launches++;
+    CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
+    return PINN_OK;
+}
+
+static int run_allreduce(pinn_ctx* c) {
+    if (c->cfg.nranks <= 1 || !c->comm) return PINN_OK;
+    const int rc = g_nccl.AllReduce(c->d_gbuf, c->d_gbuf, (size_t)c->nd.P + 3, kNcclFloat32, kNcclSum, c->comm, c->stream);
+    if (rc != 0) return fail(c, PINN_ERR_NCCL, std::string("pinn_train_step: ncclAllReduce -> ") +
+                                                   (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    return PINN_OK;
+}
+
+static int run_apply(pinn_ctx* c, int apply) {
+    adam_kernel<<<(c->nd.P + 255) / 256, 256, 0, c->stream>>>(c->nd, c->adam, c->d_params, c->d_paramsT, c->d_m, c->d_v,
+                                                            c->d_gbuf, c->d_step, c->d_loss, c->d_flag, apply);
+    c->launches++;
+    CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
+    if (apply) c->host_step++;
+    return PINN_OK;
+}
+
+static int read_out(pinn_ctx* c, pinn_step_out* out) {
+    if (!out) return PINN_OK;
+    CUDA_TRY(c, "pinn_train_step", cudaMemcpyAsync(c->h_pinned, c->d_loss, 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, "pinn_train_step", cudaMemcpyAsync(c->h_pinned + 4, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, "pinn_train_step", cudaStreamSynchronize(c->stream));
+    out->loss = c->h_pinned[0]; out->mse_residual = c->h_pinned[1];
+    out->mse_boundary = c->h_pinned[2]; out->mse_initial = c->h_pinned[3];
+    out->step = c->host_step;
+    int flag; memcpy(&flag, c->h_pinned + 4, sizeof(int));
+    if (flag == PINN_ERR_DEVICE_OVERFLOW) {
+        cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream);
+        return fail(c, PINN_ERR_DEVICE_OVERFLOW, "network::train_step: overflow");   // reference runtime.cuh:17-38 text
+    }
+    return PINN_OK;
+}
+
+static void drain_profile(pinn_ctx* c) {
+    for (auto& pr : c->pending) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+            c->kernel_ms += ms; c->kernel_count++;
+        }
+        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    c->pending.clear();
+}
+
+extern "C" {
+
+int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
+    if (!out || !cfg) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != PINN_ABI_VERSION) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: abi_version mismatch");
+    if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: invalid rank / nranks");
+    if (cfg->precision != PINN_PREC_FP32) return fail(nullptr, PINN_ERR_UNSUPPORTED, "pinn_create: only PINN_PREC_FP32 is built in this round");
+    NetDims nd; std::string why;
+    if (!make_dims(cfg, &nd, why)) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: " + why);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, PINN_ERR_NO_DEVICE, "pinn_create: no CUDA device (this library has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: device ordinal out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, PINN_ERR_NO_DEVICE, "pinn_create: device is not sm_100 (Blackwell B200); kernels are built for sm_100a only");
+
+    pinn_ctx* c = new pinn_ctx();
+    c->cfg = *cfg; c->nd = nd;
+    auto bail = [&](int rc) { g_create_error = c->err; pinn_destroy(c); return rc; };
+#define TRY_C(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { c->err = std::string("pinn_create: ") + #call + " -> " + cudaGetErrorString(e_); return bail(PINN_ERR_CUDA); } } while (0)
+    TRY_C(cudaSetDevice(cfg->device));
+    TRY_C(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    int rc = configure_kernels(c);
+    if (rc) return bail(rc);
+
+    const uint64_t counts[3] = {cfg->n_interior, cfg->n_boundary, cfg->n_initial};
+    const float lambdas[3] = {cfg->lambda_r, cfg->lambda_b, cfg->lambda_0};
+    c->seeds[0] = cfg->seed_interior; c->seeds[1] = cfg->seed_boundary; c->seeds[2] = cfg->seed_initial;
+    for (int k = 0; k < 3; k++) {
+        uint64_t b, e;
+        pinn_shard_range(counts[k], cfg->rank, cfg->nranks, &b, &e);
+        c->begin[k] = b; c->cap[k] = e - b; c->n_local[k] = e - b;
+        c->scale[k] = counts[k] ? (float)(2.0 * (double)lambdas[k] / (double)counts[k]) : 0.0f;
+        if (c->cap[k]) TRY_C(cudaMalloc(&c->d_x[k], c->cap[k] * nd.d_in * sizeof(float)));
+    }
+    c->adam.lr = cfg->lr; c->adam.beta1 = cfg->beta1; c->adam.beta2 = cfg->beta2; c->adam.eps = cfg->eps;
+    c->adam.lambda_r = cfg->lambda_r; c->adam.lambda_b = cfg->lambda_b; c->adam.lambda_0 = cfg->lambda_0;
+    c->adam.inv_nf = counts[0] ? 1.0 / (double)counts[0] : 0.0;
+    c->adam.inv_nb = counts[1] ? 1.0 / (double)counts[1] : 0.0;
+    c->adam.inv_n0 = counts[2] ? 1.0 / (double)counts[2] : 0.0;
+
+    // grids are bounded by the tile counts, so size the per-CTA scratch by what can actually launch
+    const int tiles_f = tiles_of(c->cap[0], c->TP);
+    const int tiles_v = tiles_of(c->cap[1], c->TP) + tiles_of(c->cap[2], c->TP);
+    int gmax_f = tiles_f < c->grid_cap_full ? tiles_f : c->grid_cap_full;
+    int gmax_v = tiles_v < c->grid_cap_val ? tiles_v : c->grid_cap_val;
+    // evaluation calls (pinn_forward / pinn_residual) may use the full grid caps
+    gmax_f = c->grid_cap_full; gmax_v = c->grid_cap_val;
+    c->nrows_cta = gmax_f > gmax_v ? gmax_f : gmax_v;
+    c->stash_per_cta = (long long)nd.L * nd.C * nd.H * c->TP;
+    const size_t P = nd.P;
+    TRY_C(cudaMalloc(&c->d_params, P * sizeof(float)));
+    TRY_C(cudaMalloc(&c->d_paramsT, P * sizeof(float)));
+    TRY_C(cudaMalloc(&c->d_m, P * sizeof(float)));
+    TRY_C(cudaMalloc(&c->d_v, P * sizeof(float)));
+    TRY_C(cudaMalloc(&c->d_gbuf, (size_t)nd.PP * sizeof(float)));
+    TRY_C(cudaMalloc(&c->d_partial, (size_t)c->nrows_cta * c->nslot * nd.PP * sizeof(float)));
+    TRY_C(cudaMalloc(&c->d_stash, (size_t)c->nrows_cta * c->stash_per_cta * sizeof(float)));
+    TRY_C(cudaMalloc(&c->d_loss, 4 * sizeof(float)));
+    TRY_C(cudaMalloc(&c->d_step, sizeof(unsigned long long)));
+    TRY_C(cudaMalloc(&c->d_flag, sizeof(int)));
+    TRY_C(cudaMallocHost(&c->h_pinned, 8 * sizeof(float)));
+    TRY_C(cudaMemsetAsync(c->d_m, 0, P * sizeof(float), c->stream));
+    TRY_C(cudaMemsetAsync(c->d_v, 0, P * sizeof(float), c->stream));
+    TRY_C(cudaMemsetAsync(c->d_gbuf, 0, (size_t)nd.PP * sizeof(float), c->stream));
+    TRY_C(cudaMemsetAsync(c->d_partial, 0, (size_t)c->nrows_cta * c->nslot * nd.PP * sizeof(float), c->stream));
+    TRY_C(cudaMemsetAsync(c->d_loss, 0, 4 * sizeof(float), c->stream));
+    TRY_C(cudaMemsetAsync(c->d_step, 0, sizeof(unsigned long long), c->stream));
+    TRY_C(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+#undef TRY_C
+    std::vector<float> w;
+    host_init_params(nd, cfg->seed_weights, w);
+    *out = c;
+    rc = pinn_set_params(c, w.data(), w.size(), 1);
+    if (rc) { *out = nullptr; return bail(rc); }
+    rc = pinn_sample_points(c);
+    if (rc) { *out = nullptr; return bail(rc); }
+    return PINN_OK;
+}
+
+void pinn_destroy(pinn_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    drain_profile(c);
+    if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
+    for (int k = 0; k < 3; k++) cudaFree(c->d_x[k]);
+    cudaFree(c->d_params); cudaFree(c->d_paramsT); cudaFree(c->d_m); cudaFree(c->d_v);
+    cudaFree(c->d_gbuf); cudaFree(c->d_partial); cudaFree(c->d_stash); cudaFree(c->d_loss);
+    cudaFree(c->d_step); cudaFree(c->d_flag);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int pinn_set_params(pinn_ctx* c, const float* flat, size_t n, int reset_optimizer) {
+    if (!c || !flat) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_set_params: null argument");
+    if (n != (size_t)c->nd.P) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_set_params: size mismatch - " + std::to_string(n) + " != " + std::to_string(c->nd.P));
+    CUDA_TRY(c, "pinn_set_params", cudaSetDevice(c->cfg.device));
+    CUDA_TRY(c, "pinn_set_params", cudaMemcpyAsync(c->d_params, flat, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    transpose_params_kernel<<<(c->nd.P + 255) / 256, 256, 0, c->stream>>>(c->nd, c->d_params, c->d_paramsT);
+    c->launches++;
+    if (reset_optimizer) {
+        CUDA_TRY(c, "pinn_set_params", cudaMemsetAsync(c->d_m, 0, n * sizeof(float), c->stream));
+        CUDA_TRY(c, "pinn_set_params", cudaMemsetAsync(c->d_v, 0, n * sizeof(float), c->stream));
+        CUDA_TRY(c, "pinn_set_params", cudaMemsetAsync(c->d_step, 0, sizeof(unsigned long long), c->stream));
+        c->host_step = 0;
+    }
+    CUDA_TRY(c, "pinn_set_params", cudaStreamSynchronize(c->stream));
+    return PINN_OK;
+}
+
+static int copy_out(pinn_ctx* c, const char* fn, const float* src, float* dst, size_t n) {
+    if (!c || !dst) return fail(c, PINN_ERR_INVALID_ARGUMENT, std::string(fn) + ": null argument");
+    if (n != (size_t)c->nd.P) return fail(c, PINN_ERR_INVALID_ARGUMENT, std::string(fn) + ": size mismatch");
+    CUDA_TRY(c, fn, cudaSetDevice(c->cfg.device));
+    CUDA_TRY(c, fn, cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, fn, cudaStreamSynchronize(c->stream));
+    return PINN_OK;
+}
+int pinn_get_params(pinn_ctx* c, float* flat, size_t n) { return copy_out(c, "pinn_get_params", c ? c->d_params : nullptr, flat, n); }
+int pinn_get_grads(pinn_ctx* c, float* flat, size_t n) { return copy_out(c, "pinn_get_grads", c ? c->d_gbuf : nullptr, flat, n); }
+
+int pinn_get_optimizer(pinn_ctx* c, float* m, float* v, size_t n, uint64_t* step) {
+    int rc = copy_out(c, "pinn_get_optimizer", c ? c->d_m : nullptr, m, n);
+    if (rc) return rc;
+    rc = copy_out(c, "pinn_get_optimizer", c->d_v, v, n);
+    if (rc) return rc;
+    if (step) *step = c->host_step;
+    return PINN_OK;
+}
+
+int pinn_set_optimizer(pinn_ctx* c, const float* m, const float* v, size_t n, uint64_t step) {
+    if (!c || !m || !v) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_set_optimizer: null argument");
+    if (n != (size_t)c->nd.P) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_set_optimizer: size mismatch");
+    CUDA_TRY(c, "pinn_set_optimizer", cudaSetDevice(c->cfg.device));
+    unsigned long long s = step;
+    CUDA_TRY(c, "pinn_set_optimizer", cudaMemcpyAsync(c->d_m, m, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, "pinn_set_optimizer", cudaMemcpyAsync(c->d_v, v, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, "pinn_set_optimizer", cudaMemcpyAsync(c->d_step, &s, sizeof(s), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, "pinn_set_optimizer", cudaStreamSynchronize(c->stream));
+    c->host_step = step;
+    return PINN_OK;
+}
+
+int pinn_sample_points(pinn_ctx* c) {
+    if (!c) return PINN_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(c, "pinn_sample_points", cudaSetDevice(c->cfg.device));
+    for (int k = 0; k < 3; k++) {
+        c->n_local[k] = c->cap[k];
+        if (!c->cap[k]) continue;
+        const uint64_t n = c->cap[k];
+        sample_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->nd, k, c->seeds[k], c->begin[k], n, c->d_x[k]);
+        c->launches++;
+    }
+    CUDA_TRY(c, "pinn_sample_points", cudaGetLastError());
+    return PINN_OK;
+}
+
+int pinn_resample_points(pinn_ctx* c, uint64_t si, uint64_t sb, uint64_t s0) {
+    if (!c) return PINN_ERR_INVALID_ARGUMENT;
+    c->seeds[0] = si; c->seeds[1] = sb; c->seeds[2] = s0;
+    return pinn_sample_points(c);
+}
+
+int pinn_set_points(pinn_ctx* c, int set, const float* x, size_t n) {
+    if (!c || set < 0 || set > 2 || (!x && n)) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_set_points: invalid argument");
+    if (n > c->cap[set]) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_set_points: more points than the shard fixed at create time");
+    CUDA_TRY(c, "pinn_set_points", cudaSetDevice(c->cfg.device));
+    if (n) CUDA_TRY(c, "pinn_set_points", cudaMemcpyAsync(c->d_x[set], x, n * c->nd.d_in * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    c->n_local[set] = n;
+    return PINN_OK;
+}
+
+int pinn_get_points(pinn_ctx* c, int set, float* x, size_t n) {
+    if (!c || set < 0 || set > 2 || (!x && n)) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_get_points: invalid argument");
+    if (n > c->n_local[set]) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_get_points: more points than resident");
+    CUDA_TRY(c, "pinn_get_points", cudaSetDevice(c->cfg.device));
+    if (n) CUDA_TRY(c, "pinn_get_points", cudaMemcpyAsync(x, c->d_x[set], n * c->nd.d_in * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, "pinn_get_points", cudaStreamSynchronize(c->stream));
+    return PINN_OK;
+}
+
+size_t pinn_local_count(const pinn_ctx* c, int set) { return (c && set >= 0 && set <= 2) ? (size_t)c->n_local[set] : 0; }
+
+int pinn_step_local(pinn_ctx* c) {
+    if (!c) return PINN_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(c, "pinn_step_local", cudaSetDevice(c->cfg.device));
+    return run_local(c, 1);
+}
+
+int pinn_step_apply(pinn_ctx* c, pinn_step_out* out) {
+    if (!c) return PINN_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(c, "pinn_step_apply", cudaSetDevice(c->cfg.device));
+    int rc = run_apply(c, 1);
+    if (rc) return rc;
+    return read_out(c, out);
+}
+
+int pinn_train_step(pinn_ctx* c, pinn_step_out* out) {
+    if (!c) return PINN_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(c, "pinn_train_step", cudaSetDevice(c->cfg.device));
+    int rc = run_local(c, 1);
+    if (!rc) rc = run_allreduce(c);
+    if (!rc) rc = run_apply(c, 1);
+    if (!rc) rc = read_out(c, out);
+    return rc;
+}
+
+int pinn_train_steps(pinn_ctx* c, int k, pinn_step_out* out) {
+    if (!c || k < 1) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_train_steps: k must be >= 1");
+    CUDA_TRY(c, "pinn_train_steps", cudaSetDevice(c->cfg.device));
+    for (int s = 0; s < k; s++) {
+        int rc = run_local(c, 1);
+        if (!rc) rc = run_allreduce(c);
+        if (!rc) rc = run_apply(c, 1);
+        if (rc) return rc;
+    }
+    return read_out(c, out);
+}
+
+int pinn_train_step_host(pinn_ctx* c, const float* x_interior, size_t n, pinn_step_out* out) {
+    if (!c) return PINN_ERR_INVALID_ARGUMENT;
+    int rc = pinn_set_points(c, PINN_SET_INTERIOR, x_interior, n);
+    if (rc) return rc;
+    return pinn_train_step(c, out);
+}
+
+int pinn_loss_grad(pinn_ctx* c, pinn_step_out* out) {
+    if (!c) return PINN_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(c, "pinn_loss_grad", cudaSetDevice(c->cfg.device));
+    int rc = run_local(c, 0);
+    if (!rc) rc = run_allreduce(c);
+    if (!rc) rc = run_apply(c, 0);
+    if (!rc) rc = read_out(c, out);
+    return rc;
+}
+
+static int eval_common(pinn_ctx* c, const char* fn, bool full, const float* x, float* y, float* r, size_t n) {
+    if (!c || (!x && n)) return fail(c, PINN_ERR_INVALID_ARGUMENT, std::string(fn) + ": null argument");
+    if (n == 0) return PINN_OK;
+    CUDA_TRY(c, fn, cudaSetDevice(c->cfg.device));
+    const NetDims& nd = c->nd;
+    const int nc = full ? nd.C : 1;
+    float *dx = nullptr, *dy = nullptr, *dr = nullptr;
+    CUDA_TRY(c, fn, cudaMallocAsync(&dx, n * nd.d_in * sizeof(float), c->stream));
+    CUDA_TRY(c, fn, cudaMallocAsync(&dy, n * nd.d_out * nc * sizeof(float), c->stream));
+    if (full) CUDA_TRY(c, fn, cudaMallocAsync(&dr, n * nd.n_res * sizeof(float), c->stream));
+    CUDA_TRY(c, fn, cudaMemcpyAsync(dx, x, n * nd.d_in * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    PointSet s{};
+    s.x = dx; s.n = n; s.scale = 0.0f; s.set = full ? PINN_SET_INTERIOR : PINN_SET_BOUNDARY; s.ntiles = tiles_of(n, c->TP);
+    int rc = launch_fused(c, full, &s, 1, 1, dy, dr);
+    if (rc) return rc;
+    if (y) CUDA_TRY(c, fn, cudaMemcpyAsync(y, dy, n * nd.d_out * nc * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (r && full) CUDA_TRY(c, fn, cudaMemcpyAsync(r, dr, n * nd.n_res * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    cudaFreeAsync(dx, c->stream); cudaFreeAsync(dy, c->stream);
+    if (dr) cudaFreeAsync(dr, c->stream);
+    CUDA_TRY(c, fn, cudaStreamSynchronize(c->stream));
+    return PINN_OK;
+}
+
+int pinn_forward(pinn_ctx* c, const float* x, float* y, size_t n) { return eval_common(c, "pinn_forward", false, x, y, nullptr, n); }
+int pinn_residual(pinn_ctx* c, const float* x, float* y, float* r, size_t n) { return eval_common(c, "pinn_residual", true, x, y, r, n); }
+
+int pinn_synchronize(pinn_ctx* c) {
+    if (!c) return PINN_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(c, "pinn_synchronize", cudaSetDevice(c->cfg.device));
+    CUDA_TRY(c, "pinn_synchronize", cudaStreamSynchronize(c->stream));
+    return PINN_OK;
+}
+
+int pinn_comm_unique_id(void* id128) {
+    std::string err;
+    if (!id128) return PINN_ERR_INVALID_ARGUMENT;
+    if (!nccl_load(err)) return fail(nullptr, PINN_ERR_NCCL, "pinn_comm_unique_id: " + err);
+    const int rc = g_nccl.GetUniqueId(id128);
+    return rc == 0 ? PINN_OK : fail(nullptr, PINN_ERR_NCCL, "pinn_comm_unique_id: ncclGetUniqueId failed");
+}
+
+int pinn_comm_init(pinn_ctx* c, const void* id128) {
+    if (!c || !id128) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_comm_init: null argument");
+    if (c->cfg.nranks <= 1) return PINN_OK;
+    std::string err;
+    if (!nccl_load(err)) return fail(c, PINN_ERR_NCCL, "pinn_comm_init: " + err);
+    CUDA_TRY(c, "pinn_comm_init", cudaSetDevice(c->cfg.device));
+    NcclId id; memcpy(&id, id128, sizeof(id));
+    const int rc = g_nccl.CommInitRank(&c->comm, c->cfg.nranks, id, c->cfg.rank);
+    if (rc != 0) return fail(c, PINN_ERR_NCCL, std::string("pinn_comm_init: ncclCommInitRank -> ") +
+                                                   (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    return PINN_OK;
+}
+
+void* pinn_grad_buffer(pinn_ctx* c, size_t* n_floats) {
+    if (!c) return nullptr;
+    if (n_floats) *n_floats = (size_t)c->nd.P + 3;
+    return c->d_gbuf;
+}
+void* pinn_stream(pinn_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int pinn_profile_enable(pinn_ctx* c, int enable) {
+    if (!c) return PINN_ERR_INVALID_ARGUMENT;
+    c->prof = enable != 0;
+    return PINN_OK;
+}
+
+int pinn_profile_get(pinn_ctx* c, pinn_profile* out, int reset) {
+    if (!c || !out) return PINN_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->cfg.device);
+    drain_profile(c);
+    out->launches = c->launches; out->step_kernel_ms = c->kernel_ms; out->step_kernel_count = c->kernel_count;
+    out->grid = c->last_grid; out->block = c->threads; out->smem_bytes = c->smem_full; out->kernel_id = c->kernel_id;
+    if (reset) { c->launches = 0; c->kernel_ms = 0.0; c->kernel_count = 0; }
+    return PINN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+"""CPU tests of the C-ABI boundary: the shared library loads, exports every symbol the header
+declares, its host-only helpers agree with the oracle, and it FAILS LOUDLY without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import ROOT
+
+
+@pytest.fixture(scope="module")
+def P():
+    from __graft_entry__ import build, load
+    if not os.path.exists(os.path.join(ROOT, "cuda-pinn_b200", "libpinn_b200.so")):
+        build()
+    return load()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "pinn_abi.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pinn_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(P):
+    L = P.lib()
+    declared = header_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(L, name), f"libpinn_b200.so does not export {name}"
+    assert sorted(P.ABI_SYMBOLS) == declared, "python binding and header disagree on the ABI surface"
+
+
+def test_config_struct_layout_matches_oracle_mirror(P, oracle):
+    assert C.sizeof(P.PinnConfig) == C.sizeof(oracle.PinnConfig) == 128
+    assert [f[0] for f in P.PinnConfig._fields_] == [f[0] for f in oracle.PinnConfig._fields_]
+
+
+@pytest.mark.parametrize("which", [1, 2, 3, 4, 5])
+def test_default_configs_match_baseline(P, oracle, which):
+    cfg = P.default_config(which)
+    ocfg = oracle.baseline_config(which)
+    for f, _ in P.PinnConfig._fields_:
+        a, b = getattr(cfg, f), getattr(ocfg, f)
+        assert a == pytest.approx(b), f
+    assert P.lib().pinn_num_params(C.byref(cfg)) == oracle.num_params(ocfg) == [0, 3021, 3021, 12737, 83201, 462339][which]
+    assert P.lib().pinn_num_channels(C.byref(cfg)) == oracle.num_channels(ocfg) == [0, 4, 4, 5, 6, 6][which]
+
+
+def test_shard_ranges_bit_exact_with_oracle(P, oracle):
+    for n in (0, 1, 31, 25600, (1 << 26) + 7, (1 << 40) + 12345):
+        for R in (1, 2, 3, 4, 8):
+            prev = 0
+            for r in range(R):
+                b, e = P.shard_range(n, r, R)
+                assert (b, e) == oracle.shard_range(n, r, R) == ((r * n) // R, ((r + 1) * n) // R)
+                assert b == prev
+                prev = e
+            assert prev == n
+
+
+def test_no_gpu_means_loud_failure_not_fallback(P):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(P.PinnError) as ei:
+        P.Network(P.default_config(1))
+    assert ei.value.code == 4 and "no CPU fallback" in str(ei.value)
+
+
+def test_invalid_configs_are_rejected_with_reference_style_messages(P):
+    import torch
+    cfg = P.default_config(1, width=18)
+    with pytest.raises(P.PinnError) as ei:
+        P.Network(cfg)
+    # width check precedes the device probe, so this also holds on the CPU box
+    assert ei.value.code == 3 and "pinn_create: width must be a multiple of 4" in str(ei.value)
+    with pytest.raises(P.PinnError) as ei:
+        P.Network(P.default_config(1, d_in=3))
+    assert "d_in does not match the pde" in str(ei.value)
+    with pytest.raises(P.PinnError):
+        P.Network(P.default_config(1, rank=2, nranks=2))
+    assert P.lib().pinn_num_params(C.byref(P.default_config(1, depth=0))) == 0
+
+
+def test_product_sources_never_touch_the_oracle():
+    """The product path may not import, link or execute anything under oracle/."""
+    bad = []
+    for base in ("cuda-pinn_b200", "include", "src"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"import\s+oracle|from\s+oracle|liboracle|oracle/|oracle\.|include.*oracle|dlopen.*oracle", txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad

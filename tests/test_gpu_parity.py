@@ -1,0 +1,210 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/pinn_abi.h), against the
+CPU oracle and the committed torch.autograd golden fixtures.
+
+Tolerances (FP32 path, stated per north_star): loss 1e-5 relative; gradient 1e-4 relative to its
+max-norm for a single evaluation; after 100 Adam steps loss 1e-5 relative and parameters 1e-4
+(absolute, parameters are O(1)) against the float64 oracle.  Sampling and shard indices: bit-exact.
+"""
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_CASES, cfg_from_dict, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    from __graft_entry__ import load
+    return load()
+
+
+def pcfg(P, ocfg, **kw):
+    """product-side pinn_config with the same fields as an oracle-side config"""
+    c = P.PinnConfig()
+    for f, _ in P.PinnConfig._fields_:
+        setattr(c, f, getattr(ocfg, f))
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+# ------------------------------------------------------------------ sampling: bit-exact
+@pytest.mark.parametrize("pde", [0, 1, 2, 3, 4])
+def test_sampler_bit_exact(P, oracle, pde):
+    ocfg = oracle.make_config(pde, 16, 2, 5000, 333, 0 if pde == 1 else 257)
+    with P.Network(pcfg(P, ocfg)) as net:
+        for k in range(3):
+            got = net.get_points(k)
+            assert np.array_equal(got.view(np.uint32), oracle.sample(ocfg, k).view(np.uint32)), (pde, k)
+
+
+@pytest.mark.parametrize("R", [2, 3, 8])
+def test_shards_bit_exact_for_any_rank_count(P, oracle, R):
+    ocfg = oracle.make_config(oracle.PDE_NAVIER_STOKES, 16, 2, 10007, 301, 299)
+    whole = [oracle.sample(ocfg, k) for k in range(3)]
+    parts = [[], [], []]
+    for r in range(R):
+        with P.Network(pcfg(P, ocfg, rank=r, nranks=R)) as net:
+            for k in range(3):
+                b, e = P.shard_range(oracle.set_count(ocfg, k), r, R)
+                assert net.local_count(k) == e - b
+                parts[k].append(net.get_points(k))
+    for k in range(3):
+        assert np.array_equal(np.concatenate(parts[k]).view(np.uint32), whole[k].view(np.uint32))
+
+
+def test_glorot_init_bit_exact(P, oracle):
+    for which in (1, 3):
+        ocfg = oracle.baseline_config(which, n_interior=64)
+        with P.Network(pcfg(P, ocfg)) as net:
+            assert np.array_equal(net.get_params().view(np.uint32), oracle.init_params(ocfg).view(np.uint32))
+
+
+# ------------------------------------------------------------------ loss + gradient vs goldens
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_loss_and_gradient_match_torch_autograd_golden(P, oracle, name):
+    d, z = load_golden(name)
+    ocfg = cfg_from_dict(oracle, d)
+    with P.Network(pcfg(P, ocfg)) as net:
+        for k, key in ((0, "xf"), (1, "xb"), (2, "x0")):
+            assert np.array_equal(net.get_points(k).view(np.uint32), z[key].view(np.uint32))
+        net.set_params(z["params"])
+        out = net.loss_grad()
+        g = net.get_grads()
+    assert abs(out["loss"] - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
+    sums = z["sums"]
+    assert out["mse_residual"] == pytest.approx(sums[0] / d["n_interior"], rel=1e-5)
+    assert out["mse_boundary"] == pytest.approx(sums[1] / d["n_boundary"], rel=1e-5)
+    if d["n_initial"]:
+        assert out["mse_initial"] == pytest.approx(sums[2] / d["n_initial"], rel=1e-5)
+    assert rel_err(g, z["grad"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_taylor_channels_and_residuals_match_golden(P, oracle, name):
+    d, z = load_golden(name)
+    ocfg = cfg_from_dict(oracle, d)
+    with P.Network(pcfg(P, ocfg)) as net:
+        net.set_params(z["params"])
+        Y, r = net.residual(z["xf"])
+        y = net.forward(z["xf"])
+    assert rel_err(Y, z["Y"]) < 2e-5
+    assert rel_err(r, z["r"]) < 2e-5
+    assert rel_err(y, z["Y"][:, :, 0]) < 1e-5
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_adam_steps_match_golden(P, oracle, name):
+    d, z = load_golden(name)
+    ocfg = cfg_from_dict(oracle, d)
+    steps = len(z["traj_loss"])
+    with P.Network(pcfg(P, ocfg)) as net:
+        net.set_params(z["params"])
+        losses = [net.train_step()["loss"] for _ in range(steps)]
+        w = net.get_params()
+        m, v, t = net.get_optimizer()
+    assert t == steps
+    assert rel_err(losses, z["traj_loss"]) < 1e-5
+    assert np.abs(w - z["params_after"]).max() < 1e-5
+    assert rel_err(m, z["adam_m"]) < 1e-4 and rel_err(v, z["adam_v"]) < 2e-4
+
+
+# ------------------------------------------------------------------ the baseline networks vs the oracle
+@pytest.mark.parametrize("which,n", [(1, 4096), (2, 25600), (3, 8192), (4, 2048), (5, 1024)])
+def test_baseline_networks_loss_grad_vs_oracle(P, oracle, which, n):
+    ocfg = oracle.baseline_config(which, n_interior=n, n_boundary=max(256, n // 32),
+                                  n_initial=0 if which == 3 else max(256, n // 32))
+    with P.Network(pcfg(P, ocfg)) as net:
+        w = net.get_params()
+        out = net.loss_grad()
+        g = net.get_grads()
+    xs = [oracle.sample(ocfg, k) for k in range(3)]
+    g_ref, s_ref = oracle.loss_grad(ocfg, w.astype(np.float64), *xs)
+    loss_ref = oracle.loss_from_sums(ocfg, s_ref)[0]
+    assert abs(out["loss"] - loss_ref) <= 1e-5 * abs(loss_ref)
+    assert rel_err(g, g_ref) < 1e-4
+
+
+def test_100_adam_steps_c1_against_float64_oracle(P, oracle):
+    """north_star tolerance: 1e-5 relative on the loss, 1e-4 on the parameters after 100 steps."""
+    ocfg = oracle.baseline_config(1)
+    with P.Network(pcfg(P, ocfg)) as net:
+        w0 = net.get_params()
+        losses = np.array([net.train_step()["loss"] for _ in range(100)])
+        w = net.get_params()
+    p_ref, _, _, l_ref, _ = oracle.train(ocfg, w0.astype(np.float64), 100, dtype=np.float64)
+    assert np.abs(losses / l_ref[:, 0] - 1).max() < 1e-5
+    assert np.abs(w - p_ref).max() < 1e-4
+
+
+# ------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("nf,nb,n0", [(1, 1, 1), (31, 33, 1), (97, 5, 64), (1000, 256, 0)])
+def test_ragged_and_tiny_point_sets(P, oracle, nf, nb, n0):
+    ocfg = oracle.make_config(oracle.PDE_HEAT, 8, 2, nf, nb, n0)
+    with P.Network(pcfg(P, ocfg)) as net:
+        w = net.get_params()
+        out = net.loss_grad()
+        g = net.get_grads()
+    xs = [oracle.sample(ocfg, k) for k in range(3)]
+    g_ref, s_ref = oracle.loss_grad(ocfg, w.astype(np.float64), *xs)
+    assert abs(out["loss"] - oracle.loss_from_sums(ocfg, s_ref)[0]) <= 1e-5 * abs(oracle.loss_from_sums(ocfg, s_ref)[0])
+    assert rel_err(g, g_ref) < 1e-4
+
+
+def test_set_points_roundtrip_and_host_step_equals_resident_step(P, oracle):
+    ocfg = oracle.make_config(oracle.PDE_BURGERS, 20, 3, 3000, 256, 256)
+    xf = oracle.sample(ocfg, 0)
+    with P.Network(pcfg(P, ocfg)) as a, P.Network(pcfg(P, ocfg)) as b:
+        o_a = a.train_step()
+        o_b = b.train_step_host(xf, len(xf))
+        assert o_a["loss"] == o_b["loss"]
+        assert np.array_equal(a.get_params().view(np.uint32), b.get_params().view(np.uint32))
+        perm = xf[::-1].copy()
+        b.set_points(0, perm)
+        assert np.array_equal(b.get_points(0), perm)
+        with pytest.raises(P.PinnError):
+            b.set_points(0, np.zeros((3001, 2), dtype=np.float32))
+
+
+def test_bit_reproducible_across_runs(P, oracle):
+    ocfg = oracle.baseline_config(1)
+    res = []
+    for _ in range(2):
+        with P.Network(pcfg(P, ocfg)) as net:
+            net.train_steps(5)
+            res.append(net.get_params())
+    assert np.array_equal(res[0].view(np.uint32), res[1].view(np.uint32))
+
+
+# ------------------------------------------------------------------ size-independent properties at full size
+def test_shard_gradients_sum_to_the_whole_c2_full_size(P, oracle):
+    """linearity over points: sum of per-rank local gradient buffers == single-rank gradient."""
+    ocfg = oracle.baseline_config(2)
+    with P.Network(pcfg(P, ocfg)) as net:
+        net.loss_grad()
+        g_whole = net.get_grads().astype(np.float64)
+    acc = np.zeros_like(g_whole)
+    for r in range(4):
+        with P.Network(pcfg(P, ocfg, rank=r, nranks=4)) as net:
+            net.step_local()
+            acc += net.get_grads().astype(np.float64)
+    assert rel_err(acc, g_whole) < 2e-6
+
+
+def test_c3_full_size_loss_is_mean_of_chunk_losses(P, oracle):
+    """1M-point Helmholtz: residual MSE over the whole set == mean of residuals returned by
+    pinn_residual on chunks (checksum of checksums), and a 4,096-point subsample matches the oracle."""
+    ocfg = oracle.baseline_config(3)
+    with P.Network(pcfg(P, ocfg)) as net:
+        out = net.loss_grad()
+        xf = net.get_points(0)
+        w = net.get_params()
+        ss = 0.0
+        for i in range(0, len(xf), 1 << 18):
+            _, r = net.residual(xf[i:i + (1 << 18)])
+            ss += float((r.astype(np.float64) ** 2).sum())
+        assert out["mse_residual"] == pytest.approx(ss / len(xf), rel=2e-6)
+        Y, r = net.residual(xf[:4096])
+    Y_ref, r_ref = oracle.residual(ocfg, w.astype(np.float64), xf[:4096])
+    assert rel_err(Y, Y_ref) < 2e-5 and rel_err(r, r_ref) < 2e-5
