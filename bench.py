@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — collocation points/s per PINN train step (fwd + residual + bwd + Adam) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1..5] [--points n] [--impl reference]
+
+One process per GPU (torchrun for N>1, NCCL); a "step" is one pass of the hot path over this rank's
+shard of the collocation set.  Prints ONE JSON line on rank 0 (contract in the task statement):
+`value` = whole-job points/s with inputs resident in HBM, `e2e` = the same through the public
+C-ABI call with HOST point buffers (pinned H2D of the step's points + D2H of the loss inside the
+timed region), `roofline` for the fused kernel from CUDA-event launch times measured live,
+`cpu_baseline` = the CPU oracle (port; the reference has no CPU path) on a bounded sample.
+
+--impl reference: the reference has no implementation of this path, so the arm
+times the oracle port (FP32, OpenMP, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIG_NAMES = {
+    1: "C1 builder-default Burgers 2->[20x8]->1, 4,096 pts",
+    2: "C2 1-D viscous Burgers 2->[20x8]->1, 25,600 pts",
+    3: "C3 2-D Helmholtz 2->[64x4]->1, 1,048,576 pts",
+    4: "C4 2-D Allen-Cahn 3->[128x6]->1, 16,777,216 pts",
+    5: "C5 2-D Navier-Stokes 3->[256x8]->3, 67,108,864 pts",
+}
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # CUDA-core FMA peak at max SM clock (derived)
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update({k: m[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
+        p["source"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def global_counts(which, gpus, points):
+    base = {1: 4096, 2: 25600, 3: 1 << 20, 4: 1 << 24, 5: 1 << 26}[which]
+    if points:
+        per_gpu = points
+    elif which in (4, 5):
+        per_gpu = base // 8          # the 16M / 64M-point configs are stated for 8 GPUs: 2M / 8M per GPU
+    else:
+        per_gpu = base
+    nf = per_gpu * gpus
+    nb = max(256, nf // 32)
+    n0 = 0 if which == 3 else nb
+    return nf, nb, n0, per_gpu
+
+
+def algorithmic(which):
+    """FLOPs/pt = 6*C*W (matmul only), HBM bytes/pt = 4*d_in   (BASELINE.md section 3)."""
+    C = {1: 4, 2: 4, 3: 5, 4: 6, 5: 6}[which]
+    W = {1: 2860, 2: 2860, 3: 12480, 4: 82432, 5: 460288}[which]
+    d_in = {1: 2, 2: 2, 3: 2, 4: 3, 5: 3}[which]
+    return 6 * C * W, 4 * d_in
+
+
+def run_reference(args):
+    """Reference arm: the oracle port (FP32, OpenMP over all host threads) on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    which = args.config
+    nf_full, _, _, per_gpu = global_counts(which, args.gpus, args.points)
+    flops_pt, _ = algorithmic(which)
+    cores = O.threads()
+    # bounded sample: ~0.6 s of CPU work per step at ~1.5 GFLOP/s/core effective
+    budget_pts = int(max(256, min(nf_full, 0.6 * cores * 1.5e9 / flops_pt)))
+    cfg = O.baseline_config(which, n_interior=budget_pts, n_boundary=max(256, budget_pts // 32),
+                            n_initial=0 if which == 3 else max(256, budget_pts // 32))
+    w = O.init_params(cfg)
+    _, m, v, _, _ = O.train(cfg, w, max(1, args.warmup), dtype="float32")
+    t0 = time.perf_counter()
+    _, _, _, losses, sec = O.train(cfg, w, args.steps, dtype="float32")
+    wall = time.perf_counter() - t0
+    pts_s = budget_pts * args.steps / sec
+    line = {
+        "impl": "reference", "metric": "collocation points/sec per train step (fwd+residual+bwd+Adam)",
+        "value": pts_s, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": CONFIG_NAMES[which], "points_per_gpu": per_gpu, "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": pts_s, "unit": "points/s", "cores": cores, "kind": "port",
+                         "sample": f"{budget_pts} interior points x {args.steps} steps (oracle FP32, OpenMP); "
+                                   "the reference has no implementation of this path (SURVEY.md F1)"},
+        "e2e": {"value": pts_s, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall, "final_loss": float(losses[-1, 0]),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(which, seconds=12.0):
+    from oracle import oracle as O
+    flops_pt, _ = algorithmic(which)
+    cores = O.threads()
+    pts = int(max(256, min({1: 4096, 2: 25600}.get(which, 1 << 30), 0.5 * cores * 1.5e9 / flops_pt)))
+    cfg = O.baseline_config(which, n_interior=pts, n_boundary=max(256, pts // 32),
+                            n_initial=0 if which == 3 else max(256, pts // 32))
+    w = O.init_params(cfg)
+    _, _, _, _, sec1 = O.train(cfg, w, 1, dtype="float32")
+    steps = int(max(2, min(200, seconds / max(sec1, 1e-4))))
+    _, _, _, _, sec = O.train(cfg, w, steps, dtype="float32")
+    return {"value": pts * steps / sec, "unit": "points/s", "cores": cores, "kind": "port",
+            "sample": f"{pts} interior points x {steps} steps, oracle FP32 + OpenMP ({sec:.1f} s)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", type=int, default=int(os.environ.get("PINN_BENCH_CONFIG", "2")), choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--points", type=int, default=0, help="interior points per GPU (default: the config's)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    from __graft_entry__ import load
+    P = load()
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if rank == 0:
+            print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torchrun", file=sys.stderr)
+        sys.exit(2)
+    if not torch.cuda.is_available():
+        print("bench.py: no CUDA device; the product path has no CPU fallback", file=sys.stderr)
+        sys.exit(3)
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    which = args.config
+    nf, nb, n0, per_gpu = global_counts(which, world, args.points)
+    cfg = P.default_config(which, n_interior=nf, n_boundary=nb, n_initial=n0, rank=rank, nranks=world, device=local_rank)
+    net = P.Network(cfg)
+    if world > 1:
+        box = [P.Network.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        net.comm_init(box[0])
+    stream = torch.cuda.ExternalStream(net.stream(), device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def barrier():
+        net.synchronize(); torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_steps(k, fn):
+        """k steps, each bracketed by CUDA events on the handle's stream, L2 flushed between them."""
+        evs = []
+        with torch.cuda.stream(stream):
+            for _ in range(k):
+                flush.zero_()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream); fn(); e1.record(stream)
+                evs.append((e0, e1))
+        net.synchronize(); torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    # ---- device-resident throughput ----
+    for _ in range(args.warmup):
+        net.train_step(read_loss=False)
+    barrier()
+    net.profile_enable(True); net.profile_get(reset=True)
+    sampler = ClockSampler(local_rank); sampler.start()
+    t_wall0 = time.perf_counter()
+    ms_total = timed_steps(args.steps, lambda: net.train_step(read_loss=False))
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    prof = net.profile_get(reset=True)
+    net.profile_enable(False)
+    last = net.loss_grad()
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = nf / (ms_step * 1e-3)
+
+    # ---- end to end through the public call with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        x_host = torch.from_numpy(net.get_points(0)).pin_memory()
+        n_loc = x_host.shape[0]
+        for _ in range(3):
+            net.train_step_host(x_host.data_ptr(), n_loc)
+        barrier()
+        ms_e2e = timed_steps(args.steps, lambda: net.train_step_host(x_host.data_ptr(), n_loc))
+        t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item()) / args.steps
+        e2e = {"value": nf / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(n_loc * cfg.d_in * 4), "d2h_bytes_per_step": 20,
+               "api": "pinn_train_step_host (C ABI), pinned host points, loss read back every step"}
+
+    if rank == 0:
+        pk = peaks()
+        flops_pt, bytes_pt = algorithmic(which)
+        k_ms = prof["step_kernel_ms"] / max(1, prof["step_kernel_count"])
+        n_loc0 = net.local_count(0)
+        ach_tf = n_loc0 * flops_pt / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+        ach_gb = n_loc0 * bytes_pt / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        roofline = {
+            "bound": "fp32_fma", "kernel": "fused_step_fp32 (interior)", "achieved": ach_tf, "peak": FP32_PEAK_TFLOPS,
+            "unit": "TFLOP/s", "frac": ach_tf / FP32_PEAK_TFLOPS, "traffic": None,
+            "peak_source": "derived 148 SM x 128 FMA x 2 x 1.965 GHz (CUDA-core path; no measured FP32 peak in MEASURED_PEAKS.json)",
+            "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step if ms_step else None,
+            "hbm": {"achieved": ach_gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_gb / pk["hbm_gbs"], "of": pk["source"]},
+            "tensor": {"achieved": ach_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                       "frac": ach_tf / pk["bf16_tflops_sustained"], "of": pk["source"]},
+            "flops_per_point": flops_pt, "bytes_per_point": bytes_pt, "points_per_launch": n_loc0,
+        }
+        line = {
+            "metric": "collocation points/sec per train step (fwd+residual+bwd+Adam)",
+            "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": CONFIG_NAMES[which], "points_per_gpu": per_gpu, "n_interior": nf, "n_boundary": nb,
+                       "n_initial": n0, "parallelism": f"dp{world}", "l2": "flushed (256 MiB memset) between timed steps",
+                       "kernel_id": prof["kernel_id"], "grid": prof["grid"], "block": prof["block"], "smem": prof["smem_bytes"]},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": prof["launches"], "clocks": clocks,
+            "final_loss": last["loss"], "wall_s": wall,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(which)
+        print(json.dumps(line), flush=True)
+    net.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,19 +30,31 @@ __global__ void sample_points_kernel(const NetDims nd, int set, uint64_t seed, u
     for (int k = 0; k < nd.d_in; k++) x[i * nd.d_in + k] = p[k];
 }
 
-// gbuf[i] = sum over CTA partial rows in fixed order; rows are zeroed for the next step.
-__global__ void reduce_partials_kernel(float* __restrict__ partial, int nrows, int PP, int n_out,
-                                       float* __restrict__ gbuf, unsigned long long* step, int bump) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0 && bump) *step += 1ULL;
-    if (i >= n_out) return;
+// gbuf[col] = sum over CTA partial rows in a fixed order (bit-reproducible); rows are zeroed for
+// the next step.  Block = 32 columns x 32 row lanes: lane y adds rows y, y+32, ... and the 32 lane
+// sums are combined in lane order through shared memory.
+__global__ void __launch_bounds__(1024)
+reduce_partials_kernel(float* __restrict__ partial, int nrows, int PP, int n_out,
+                       float* __restrict__ gbuf, unsigned long long* step, int bump) {
+    __shared__ float part[32][33];
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && bump) *step += 1ULL;
     float s = 0.0f;
-    for (int r = 0; r < nrows; r++) {
-        const size_t idx = (size_t)r * PP + i;
-        s += partial[idx];
-        partial[idx] = 0.0f;
+    if (col < n_out) {
+        for (int r = threadIdx.y; r < nrows; r += 32) {
+            const size_t idx = (size_t)r * PP + col;
+            s += partial[idx];
+            partial[idx] = 0.0f;
+        }
     }
-    gbuf[i] = s;
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < n_out) {
+        float t = 0.0f;
+        #pragma unroll
+        for (int y = 0; y < 32; y++) t += part[y][threadIdx.x];
+        gbuf[col] = t;
+    }
 }
 
 struct AdamArgs {
@@ -175,6 +187,7 @@ struct pinn_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
     double kernel_ms = 0.0; uint64_t kernel_count = 0, launches = 0;
     int last_grid = 0;
+    int rows_dirty = 0;               // CTA partial rows written since the last reduce
     uint64_t host_step = 0;
 };
 
@@ -366,6 +379,7 @@ static int launch_fused(pinn_ctx* c, bool full, const PointSet* sets, int nsets,
     (full ? c->kern_full : c->kern_val)<<<grid, c->threads, full ? c->smem_full : c->smem_val, c->stream>>>(c->nd, a);
     if (timed) { cudaEventRecord(e1, c->stream); c->pending.emplace_back(e0, e1); }
     if (full) c->last_grid = grid;
+    if (mode == 0 && grid > c->rows_dirty) c->rows_dirty = grid;
     c->launches++;
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
     return PINN_OK;
@@ -384,8 +398,9 @@ static int run_local(pinn_ctx* c, int bump_step) {
     }
     if (nv) { rc = launch_fused(c, false, v, nv, 0, nullptr, nullptr); if (rc) return rc; }
     const int n_out = c->nd.P + 3;
-    reduce_partials_kernel<<<(n_out + 255) / 256, 256, 0, c->stream>>>(c->d_partial, c->nrows_cta * c->nslot, c->nd.PP,
-                                                                     n_out, c->d_gbuf, c->d_step, bump_step);
+    reduce_partials_kernel<<<(n_out + 31) / 32, dim3(32, 32), 0, c->stream>>>(c->d_partial, c->rows_dirty * c->nslot, c->nd.PP,
+                                                                            n_out, c->d_gbuf, c->d_step, bump_step);
+    c->rows_dirty = 0;
     c->launches++;
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
     return PINN_OK;
