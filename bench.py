@@ -173,6 +173,10 @@ def main():
     ap.add_argument("--config", type=int, default=int(os.environ.get("PINN_BENCH_CONFIG", "2")), choices=[1, 2, 3, 4, 5])
     ap.add_argument("--points", type=int, default=0, help="interior points per GPU (default: the config's)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("PINN_BENCH_PRECISION", "auto"),
+                    choices=["auto", "fp32", "bf16x3", "bf16"],
+                    help="contraction arithmetic: fp32 CUDA cores | bf16x3 / bf16 tcgen05 (width 64/128/256); "
+                         "auto = fp32 for width < 64, bf16x3 for 64/128, bf16 for 256")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -204,7 +208,13 @@ def main():
 
     which = args.config
     nf, nb, n0, per_gpu = global_counts(which, world, args.points)
-    cfg = P.default_config(which, n_interior=nf, n_boundary=nb, n_initial=n0, rank=rank, nranks=world, device=local_rank)
+    width = {1: 20, 2: 20, 3: 64, 4: 128, 5: 256}[which]
+    prec_name = args.precision
+    if prec_name == "auto":
+        prec_name = "fp32" if width < 64 else ("bf16x3" if width <= 128 else "bf16")
+    prec = {"fp32": P.PREC_FP32, "bf16x3": P.PREC_BF16X3, "bf16": P.PREC_BF16}[prec_name]
+    cfg = P.default_config(which, n_interior=nf, n_boundary=nb, n_initial=n0, rank=rank, nranks=world,
+                           device=local_rank, precision=prec)
     net = P.Network(cfg)
     if world > 1:
         box = [P.Network.comm_unique_id() if rank == 0 else None]
@@ -276,10 +286,20 @@ def main():
         n_loc0 = net.local_count(0)
         ach_tf = n_loc0 * flops_pt / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
         ach_gb = n_loc0 * bytes_pt / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        tensor_path = prec_name != "fp32"
+        mma_mult = 3 if prec_name == "bf16x3" else 1     # issued tensor FLOPs per algorithmic FLOP
+        if tensor_path:
+            rf_bound, rf_peak = "tensor", pk["bf16_tflops_sustained"]
+            rf_src = f"{pk['source']} bf16_tflops_sustained (MEASURED_PEAKS.json); algorithmic FLOPs 6CW/pt, issued tensor FLOPs x{mma_mult}"
+            rf_kernel = "fused_step_tc (interior, tcgen05 " + prec_name + ")"
+        else:
+            rf_bound, rf_peak = "fp32_fma", FP32_PEAK_TFLOPS
+            rf_src = "derived 148 SM x 128 FMA x 2 x 1.965 GHz (CUDA-core path; no measured FP32 peak in MEASURED_PEAKS.json)"
+            rf_kernel = "fused_step_fp32 (interior)"
         roofline = {
-            "bound": "fp32_fma", "kernel": "fused_step_fp32 (interior)", "achieved": ach_tf, "peak": FP32_PEAK_TFLOPS,
-            "unit": "TFLOP/s", "frac": ach_tf / FP32_PEAK_TFLOPS, "traffic": None,
-            "peak_source": "derived 148 SM x 128 FMA x 2 x 1.965 GHz (CUDA-core path; no measured FP32 peak in MEASURED_PEAKS.json)",
+            "bound": rf_bound, "kernel": rf_kernel, "achieved": ach_tf, "peak": rf_peak,
+            "unit": "TFLOP/s", "frac": ach_tf / rf_peak, "traffic": None,
+            "peak_source": rf_src, "issued_tensor_tflops": ach_tf * mma_mult if tensor_path else 0.0,
             "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step if ms_step else None,
             "hbm": {"achieved": ach_gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_gb / pk["hbm_gbs"], "of": pk["source"]},
             "tensor": {"achieved": ach_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -290,8 +310,9 @@ def main():
             "metric": "collocation points/sec per train step (fwd+residual+bwd+Adam)",
             "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": CONFIG_NAMES[which], "points_per_gpu": per_gpu, "n_interior": nf, "n_boundary": nb,
+            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 operands (2-term split), f32 accumulate + f32 elementwise",
+                      "bf16": "bf16 operands, f32 accumulate + f32 elementwise"}[prec_name], "data": "synthetic",
+            "config": {"workload": CONFIG_NAMES[which], "precision": prec_name, "points_per_gpu": per_gpu, "n_interior": nf, "n_boundary": nb,
                        "n_initial": n0, "parallelism": f"dp{world}", "l2": "flushed (256 MiB memset) between timed steps",
                        "kernel_id": prof["kernel_id"], "grid": prof["grid"], "block": prof["block"], "smem": prof["smem_bytes"]},
             "roofline": roofline, "e2e": e2e, "gpu_launches": prof["launches"], "clocks": clocks,

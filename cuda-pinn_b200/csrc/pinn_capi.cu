@@ -13,6 +13,7 @@
 #include "../../include/pinn_abi.h"
 #include "pinn_device.cuh"
 #include "pinn_fused_fp32.cuh"
+#include "pinn_fused_tc.cuh"
 
 using namespace pinn;
 
@@ -178,6 +179,12 @@ struct pinn_ctx {
     int TP = 32, UT = 4, threads = 0, smem_full = 0, smem_val = 0, grid_cap_full = 0, grid_cap_val = 0;
     int nrows_cta = 0, nslot = 1, kernel_id = 0, num_sms = 148;
     long long stash_per_cta = 0;
+    // tensor-core path (precision != FP32): interior set only
+    typedef void (*tc_fn)(const NetDims, const TcArgs);
+    tc_fn kern_tc = nullptr;
+    __nv_bfloat16* d_wq = nullptr;
+    long long wq_term_stride = 0;
+    int nterms = 0, tc_threads = 0, tc_smem = 0, tc_tmem_cols = 0, grid_cap_tc = 0;
     AdamArgs adam{};
     void* comm = nullptr;
     std::string err;
@@ -343,6 +350,32 @@ static int configure_kernels(pinn_ctx* c) {
     int nslot = c->threads / ntiles_hidden;
     c->nslot = nslot < 1 ? 1 : (nslot > 8 ? 8 : nslot);
     c->kernel_id = (c->UT == 8 ? 10 : 0) + (c->TP == 16 ? 1 : 0);
+    if (c->cfg.precision != PINN_PREC_FP32) {
+        // tensor-core kernel for the interior set; boundary / initial points keep the FP32 kernel
+        const int nterms = c->cfg.precision == PINN_PREC_BF16X3 ? 2 : 1;
+        if (!(H == 64 || H == 128 || H == 256))
+            return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: the tensor-core path is built for width 64, 128 or 256 (use PINN_PREC_FP32)");
+        if (nd.d_in == 2 && nd.n2 == 1) c->kern_tc = nterms == 2 ? fused_step_tc<2, 1, 2> : fused_step_tc<2, 1, 1>;
+        else if (nd.d_in == 2 && nd.n2 == 2) c->kern_tc = nterms == 2 ? fused_step_tc<2, 2, 2> : fused_step_tc<2, 2, 1>;
+        else c->kern_tc = nterms == 2 ? fused_step_tc<3, 2, 2> : fused_step_tc<3, 2, 1>;
+        const int HW = H > 128 ? 128 : H;
+        c->nterms = nterms;
+        c->tc_threads = 2 * H;
+        c->tc_smem = nterms * (2 * H * 256 + HW * H * 2);
+        if (c->tc_smem > max_smem)
+            return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: PINN_PREC_BF16X3 needs width <= 128 (operand terms do not fit in shared memory)");
+        const int mt = (H + 127) / 128;
+        c->tc_tmem_cols = (H == 256) ? 512 : 2 * H;
+        (void)mt;
+        CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, c->tc_smem));
+        int occ = 0;
+        CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->kern_tc, c->tc_threads, c->tc_smem));
+        if (occ < 1) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: tensor-core kernel does not fit on an SM");
+        const int tmem_limit = 512 / c->tc_tmem_cols;
+        if (occ > tmem_limit) occ = tmem_limit;
+        c->grid_cap_tc = occ * c->num_sms;
+        c->kernel_id = 100 + nterms;
+    }
     return PINN_OK;
 }
 
@@ -368,7 +401,12 @@ static int launch_fused(pinn_ctx* c, bool full, const PointSet* sets, int nsets,
     for (int i = 0; i < nsets; i++) a.sets[i] = sets[i];
     a.partial = c->d_partial; a.stash = c->d_stash; a.nslot = c->nslot; a.stash_per_cta = c->stash_per_cta;
     a.mode = mode; a.y_out = y_out; a.r_out = r_out;
-    const int cap = full ? c->grid_cap_full : c->grid_cap_val;
+    const bool tc = full && c->kern_tc != nullptr;
+    if (tc) {                                             // 16-point tiles on the tensor-core kernel
+        total = 0;
+        for (int i = 0; i < nsets; i++) { a.sets[i].ntiles = tiles_of(a.sets[i].n, 16); total += a.sets[i].ntiles; }
+    }
+    const int cap = tc ? c->grid_cap_tc : (full ? c->grid_cap_full : c->grid_cap_val);
     const int grid = total < cap ? total : cap;
     const bool timed = c->prof && full && mode == 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -376,7 +414,13 @@ static int launch_fused(pinn_ctx* c, bool full, const PointSet* sets, int nsets,
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, c->stream);
     }
-    (full ? c->kern_full : c->kern_val)<<<grid, c->threads, full ? c->smem_full : c->smem_val, c->stream>>>(c->nd, a);
+    if (tc) {
+        TcArgs ta{};
+        ta.f = a; ta.wq = c->d_wq; ta.wq_term_stride = c->wq_term_stride; ta.tmem_cols = c->tc_tmem_cols;
+        c->kern_tc<<<grid, c->tc_threads, c->tc_smem, c->stream>>>(c->nd, ta);
+    } else {
+        (full ? c->kern_full : c->kern_val)<<<grid, c->threads, full ? c->smem_full : c->smem_val, c->stream>>>(c->nd, a);
+    }
     if (timed) { cudaEventRecord(e1, c->stream); c->pending.emplace_back(e0, e1); }
     if (full) c->last_grid = grid;
     if (mode == 0 && grid > c->rows_dirty) c->rows_dirty = grid;
@@ -406,6 +450,13 @@ static int run_local(pinn_ctx* c, int bump_step) {
     return PINN_OK;
 }
 
+static void refresh_wq(pinn_ctx* c) {
+    if (!c->d_wq) return;
+    const long long n = c->wq_term_stride;
+    pack_wq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->nd, c->d_params, c->d_wq, c->wq_term_stride, c->nterms);
+    c->launches++;
+}
+
 static int run_allreduce(pinn_ctx* c) {
     if (c->cfg.nranks <= 1 || !c->comm) return PINN_OK;
     const int rc = g_nccl.AllReduce(c->d_gbuf, c->d_gbuf, (size_t)c->nd.P + 3, kNcclFloat32, kNcclSum, c->comm, c->stream);
@@ -418,6 +469,7 @@ static int run_apply(pinn_ctx* c, int apply) {
     adam_kernel<<<(c->nd.P + 255) / 256, 256, 0, c->stream>>>(c->nd, c->adam, c->d_params, c->d_paramsT, c->d_m, c->d_v,
                                                             c->d_gbuf, c->d_step, c->d_loss, c->d_flag, apply);
     c->launches++;
+    if (apply) refresh_wq(c);
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
     if (apply) c->host_step++;
     return PINN_OK;
@@ -457,7 +509,7 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     *out = nullptr;
     if (cfg->abi_version != PINN_ABI_VERSION) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: abi_version mismatch");
     if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: invalid rank / nranks");
-    if (cfg->precision != PINN_PREC_FP32) return fail(nullptr, PINN_ERR_UNSUPPORTED, "pinn_create: only PINN_PREC_FP32 is built in this round");
+    if (cfg->precision < PINN_PREC_FP32 || cfg->precision > PINN_PREC_BF16) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: unknown precision");
     NetDims nd; std::string why;
     if (!make_dims(cfg, &nd, why)) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: " + why);
     int ndev = 0;
@@ -501,7 +553,8 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     // evaluation calls (pinn_forward / pinn_residual) may use the full grid caps
     gmax_f = c->grid_cap_full; gmax_v = c->grid_cap_val;
     c->nrows_cta = gmax_f > gmax_v ? gmax_f : gmax_v;
-    c->stash_per_cta = (long long)nd.L * nd.C * nd.H * c->TP;
+    if (c->grid_cap_tc > c->nrows_cta) c->nrows_cta = c->grid_cap_tc;
+    c->stash_per_cta = (long long)nd.L * nd.C * nd.H * c->TP;   // the tensor-core kernel (16-point tiles) needs no more
     const size_t P = nd.P;
     TRY_C(cudaMalloc(&c->d_params, P * sizeof(float)));
     TRY_C(cudaMalloc(&c->d_paramsT, P * sizeof(float)));
@@ -510,6 +563,10 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     TRY_C(cudaMalloc(&c->d_gbuf, (size_t)nd.PP * sizeof(float)));
     TRY_C(cudaMalloc(&c->d_partial, (size_t)c->nrows_cta * c->nslot * nd.PP * sizeof(float)));
     TRY_C(cudaMalloc(&c->d_stash, (size_t)c->nrows_cta * c->stash_per_cta * sizeof(float)));
+    if (c->kern_tc && nd.L >= 2) {
+        c->wq_term_stride = (long long)(nd.L - 1) * nd.H * nd.H;
+        TRY_C(cudaMalloc(&c->d_wq, (size_t)c->nterms * c->wq_term_stride * sizeof(__nv_bfloat16)));
+    }
     TRY_C(cudaMalloc(&c->d_loss, 4 * sizeof(float)));
     TRY_C(cudaMalloc(&c->d_step, sizeof(unsigned long long)));
     TRY_C(cudaMalloc(&c->d_flag, sizeof(int)));
@@ -541,7 +598,7 @@ void pinn_destroy(pinn_ctx* c) {
     for (int k = 0; k < 3; k++) cudaFree(c->d_x[k]);
     cudaFree(c->d_params); cudaFree(c->d_paramsT); cudaFree(c->d_m); cudaFree(c->d_v);
     cudaFree(c->d_gbuf); cudaFree(c->d_partial); cudaFree(c->d_stash); cudaFree(c->d_loss);
-    cudaFree(c->d_step); cudaFree(c->d_flag);
+    cudaFree(c->d_step); cudaFree(c->d_flag); cudaFree(c->d_wq);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -554,6 +611,7 @@ int pinn_set_params(pinn_ctx* c, const float* flat, size_t n, int reset_optimize
     CUDA_TRY(c, "pinn_set_params", cudaMemcpyAsync(c->d_params, flat, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     transpose_params_kernel<<<(c->nd.P + 255) / 256, 256, 0, c->stream>>>(c->nd, c->d_params, c->d_paramsT);
     c->launches++;
+    refresh_wq(c);
     if (reset_optimizer) {
         CUDA_TRY(c, "pinn_set_params", cudaMemsetAsync(c->d_m, 0, n * sizeof(float), c->stream));
         CUDA_TRY(c, "pinn_set_params", cudaMemsetAsync(c->d_v, 0, n * sizeof(float), c->stream));
@@ -762,7 +820,7 @@ int pinn_profile_get(pinn_ctx* c, pinn_profile* out, int reset) {
     cudaSetDevice(c->cfg.device);
     drain_profile(c);
     out->launches = c->launches; out->step_kernel_ms = c->kernel_ms; out->step_kernel_count = c->kernel_count;
-    out->grid = c->last_grid; out->block = c->threads; out->smem_bytes = c->smem_full; out->kernel_id = c->kernel_id;
+    out->grid = c->last_grid; out->block = c->kern_tc ? c->tc_threads : c->threads; out->smem_bytes = c->kern_tc ? c->tc_smem : c->smem_full; out->kernel_id = c->kernel_id;
     if (reset) { c->launches = 0; c->kernel_ms = 0.0; c->kernel_count = 0; }
     return PINN_OK;
 }

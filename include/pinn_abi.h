@@ -70,8 +70,9 @@ typedef enum pinn_pde {
 /* ---- arithmetic path of the dense contractions ---- */
 typedef enum pinn_precision {
     PINN_PREC_FP32   = 0, /* FP32 CUDA-core FMA (parity path; all widths) */
-    PINN_PREC_TF32X3 = 1, /* tcgen05 kind::tf32, 3-term split, FP32 accumulate (width >= 64) */
-    PINN_PREC_BF16   = 2  /* tcgen05 kind::f16 BF16 operands, FP32 accumulate (width >= 64) */
+    PINN_PREC_BF16X3 = 1, /* tcgen05 kind::f16, each operand split into two BF16 terms (hi*hi + hi*mid +
+                             mid*hi), FP32 accumulate in TMEM: near-FP32 products; width 64 or 128 */
+    PINN_PREC_BF16   = 2  /* tcgen05 kind::f16, BF16 operands, FP32 accumulate in TMEM; width 64/128/256 */
 } pinn_precision;
 
 /* Point sets of one training batch. */
