@@ -227,3 +227,54 @@ def test_c3_full_size_loss_is_mean_of_chunk_losses(P, oracle):
         Y, r = net.residual(xf[:4096])
     Y_ref, r_ref = oracle.residual(ocfg, w.astype(np.float64), xf[:4096])
     assert rel_err(Y, Y_ref) < 2e-5 and rel_err(r, r_ref) < 2e-5
+
+
+# ------------------------------------------------------------------ tensor-core path (tcgen05)
+# Tolerances are STATED per precision (the FP32 bar above applies to PINN_PREC_FP32 only):
+#   BF16X3 (two-term BF16 split, hi*hi + hi*mid + mid*hi, FP32 accumulate): loss 1e-5, gradient 5e-5
+#   BF16   (single BF16 term, FP32 accumulate):                             loss 5e-3, gradient 1e-2
+# relative to the float64 oracle (measured on B200: 3e-7..4.5e-6 and 2e-4..2e-3, scripts/tc_probe.py).
+TC_CASES = [  # pde, width, depth, n_interior
+    (1, 64, 4, 4000), (0, 64, 3, 3000), (2, 128, 6, 2000), (3, 128, 3, 1500), (3, 256, 8, 1100), (4, 64, 1, 700), (4, 128, 2, 17)]
+
+
+@pytest.mark.parametrize("pde,width,depth,n", TC_CASES)
+@pytest.mark.parametrize("prec,tol_l,tol_g", [(1, 1e-5, 5e-5), (2, 5e-3, 1e-2)])
+def test_tensor_core_path_against_float64_oracle(P, oracle, pde, width, depth, n, prec, tol_l, tol_g):
+    if prec == 1 and width > 128:
+        pytest.skip("BF16X3 operand terms do not fit in shared memory at width 256 (PINN_ERR_UNSUPPORTED)")
+    ocfg = oracle.make_config(pde, width, depth, n, 300, 0 if pde == 1 else 300)
+    xs = [oracle.sample(ocfg, k) for k in range(3)]
+    rng = np.random.default_rng(1)
+    w = (oracle.init_params(ocfg) + 0.02 * rng.standard_normal(oracle.num_params(ocfg))).astype(np.float32)
+    g_ref, s_ref = oracle.loss_grad(ocfg, w.astype(np.float64), *xs)
+    l_ref = oracle.loss_from_sums(ocfg, s_ref)[0]
+    with P.Network(pcfg(P, ocfg, precision=prec)) as net:
+        net.set_params(w)
+        out = net.loss_grad()
+        g = net.get_grads()
+        Y, r = net.residual(xs[0][:100])
+        assert net.profile_get()["kernel_id"] == 100 + (2 if prec == 1 else 1)      # the tcgen05 kernel really ran
+    assert abs(out["loss"] / l_ref - 1) < tol_l
+    assert rel_err(g, g_ref) < tol_g
+    Y_ref, _ = oracle.residual(ocfg, w.astype(np.float64), xs[0][:100])
+    assert rel_err(Y, Y_ref) < (1e-4 if prec == 1 else 5e-2)
+
+
+def test_tensor_core_bf16x3_training_tracks_the_oracle(P, oracle):
+    """30 Adam steps of the C3 network (2->[64x4]->1) on the BF16X3 tensor path vs the float64 oracle."""
+    ocfg = oracle.baseline_config(3, n_interior=4096, n_boundary=256)
+    with P.Network(pcfg(P, ocfg, precision=1)) as net:
+        w0 = net.get_params()
+        losses = np.array([net.train_step()["loss"] for _ in range(30)])
+        w = net.get_params()
+    p_ref, _, _, l_ref, _ = oracle.train(ocfg, w0.astype(np.float64), 30, dtype=np.float64)
+    assert np.abs(losses / l_ref[:, 0] - 1).max() < 1e-4
+    assert np.abs(w - p_ref).max() < 1e-4
+
+
+def test_tensor_core_rejects_unsupported_widths(P, oracle):
+    ocfg = oracle.make_config(oracle.PDE_BURGERS, 20, 2, 64)
+    with pytest.raises(P.PinnError) as ei:
+        P.Network(pcfg(P, ocfg, precision=2))
+    assert ei.value.code == 7 and "width 64, 128 or 256" in str(ei.value)
