@@ -31,21 +31,26 @@ __global__ void sample_points_kernel(const NetDims nd, int set, uint64_t seed, u
     for (int k = 0; k < nd.d_in; k++) x[i * nd.d_in + k] = p[k];
 }
 
-// gbuf[col] = sum over CTA partial rows in a fixed order (bit-reproducible); rows are zeroed for
-// the next step.  Block = 32 columns x 32 row lanes: lane y adds rows y, y+32, ... and the 32 lane
-// sums are combined in lane order through shared memory.
+// gbuf[col] = sum over the CTA partial rows of both launches of the step, in a fixed order
+// (bit-reproducible); rows are zeroed for the next step.  Block = 32 columns x 32 row lanes: lane y
+// adds rows y, y+32, ... of range A then of range B; the 32 lane sums are combined in lane order.
 __global__ void __launch_bounds__(1024)
-reduce_partials_kernel(float* __restrict__ partial, int nrows, int PP, int n_out,
+reduce_partials_kernel(float* __restrict__ part_a, int rows_a, float* __restrict__ part_b, int rows_b, int PP, int n_out,
                        float* __restrict__ gbuf, unsigned long long* step, int bump) {
     __shared__ float part[32][33];
     const int col = blockIdx.x * 32 + threadIdx.x;
     if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && bump) *step += 1ULL;
     float s = 0.0f;
     if (col < n_out) {
-        for (int r = threadIdx.y; r < nrows; r += 32) {
+        for (int r = threadIdx.y; r < rows_a; r += 32) {
             const size_t idx = (size_t)r * PP + col;
-            s += partial[idx];
-            partial[idx] = 0.0f;
+            s += part_a[idx];
+            part_a[idx] = 0.0f;
+        }
+        for (int r = threadIdx.y; r < rows_b; r += 32) {
+            const size_t idx = (size_t)r * PP + col;
+            s += part_b[idx];
+            part_b[idx] = 0.0f;
         }
     }
     part[threadIdx.y][threadIdx.x] = s;
@@ -164,7 +169,11 @@ typedef void (*fused_fn)(const NetDims, const FusedArgs);
 struct pinn_ctx {
     pinn_config cfg{};
     NetDims nd{};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: boundary/initial launch, forked per step
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;
+    uint64_t graph_key[4] = {0, 0, 0, 0}; bool graph_ok = true, capturing = false;
+    uint64_t step_launches = 0, launches_per_graph = 0;
     float *d_params = nullptr, *d_paramsT = nullptr, *d_m = nullptr, *d_v = nullptr;
     float *d_gbuf = nullptr, *d_partial = nullptr, *d_stash = nullptr, *d_loss = nullptr;
     unsigned long long* d_step = nullptr;
@@ -177,7 +186,7 @@ struct pinn_ctx {
     // launch configuration of the fused kernels
     fused_fn kern_full = nullptr, kern_val = nullptr;
     int TP = 32, UT = 4, threads = 0, smem_full = 0, smem_val = 0, grid_cap_full = 0, grid_cap_val = 0;
-    int nrows_cta = 0, nslot = 1, kernel_id = 0, num_sms = 148;
+    int rows_cap_a = 0, rows_cap_b = 0, nsplit_cap = 1, kernel_id = 0, num_sms = 148;
     long long stash_per_cta = 0;
     // tensor-core path (precision != FP32): interior set only
     typedef void (*tc_fn)(const NetDims, const TcArgs);
@@ -194,7 +203,6 @@ struct pinn_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
     double kernel_ms = 0.0; uint64_t kernel_count = 0, launches = 0;
     int last_grid = 0;
-    int rows_dirty = 0;               // CTA partial rows written since the last reduce
     uint64_t host_step = 0;
 };
 
@@ -296,11 +304,13 @@ const char* pinn_last_error(const pinn_ctx* ctx) { return ctx ? ctx->err.c_str()
 }  // extern "C"
 
 // ---- kernel selection -------------------------------------------------------------------
+// Launch bounds per variant: narrow nets (UT = 4, width <= 28, <= 224 threads) are compiled for
+// <= 64 registers so that 6 CTAs of 160 threads are resident per SM (C2: all 800 tiles in one wave).
 template <int DIN, int N2, bool FULL>
 static fused_fn pick_ut_tp(int UT, int TP) {
-    if (UT == 4 && TP == 32) return fused_step_fp32<DIN, N2, FULL, 4, 32>;
-    if (UT == 8 && TP == 32) return fused_step_fp32<DIN, N2, FULL, 8, 32>;
-    if (UT == 8 && TP == 16) return fused_step_fp32<DIN, N2, FULL, 8, 16>;
+    if (UT == 4 && TP == 32) return fused_step_fp32<DIN, N2, FULL, 4, 32, 256, 4>;
+    if (UT == 8 && TP == 32) return fused_step_fp32<DIN, N2, FULL, 8, 32, 512, 1>;
+    if (UT == 8 && TP == 16) return fused_step_fp32<DIN, N2, FULL, 8, 16, 512, 1>;
     return nullptr;
 }
 static fused_fn pick_kernel(int d_in, int n2, bool full, int UT, int TP) {
@@ -323,6 +333,7 @@ static int configure_kernels(pinn_ctx* c) {
     const int max_smem = (int)prop.sharedMemPerBlockOptin;
     const int H = nd.H, rows = (H + 3) & ~3;
     c->UT = (H % 8 == 0 && H >= 32) ? 8 : 4;
+    if (c->UT == 4 && H > 28) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: widths above 28 must be multiples of 8");
     auto smem_for = [&](int nc, int tp) { return (int)(2 * (size_t)rows * (nc * tp + 4) * sizeof(float)); };
     c->TP = 32;
     if (smem_for(nd.C, 32) > max_smem || 32 * (H / c->UT) > 512) {
@@ -332,8 +343,13 @@ static int configure_kernels(pinn_ctx* c) {
             return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: width too large for the FP32 fused kernel");
     }
     c->threads = c->TP * (H / c->UT);
-    c->smem_full = smem_for(nd.C, c->TP);
-    c->smem_val = smem_for(1, c->TP);
+    // split-dW scratch ([threads][16] floats) only where it is cheap: narrow nets, whose 4x4 dW
+    // micro-tiles are fewer than the threads of the CTA
+    c->nsplit_cap = (H <= 64) ? 8 : 1;
+    const int scratch = c->nsplit_cap > 1 ? c->threads * 16 * (int)sizeof(float) : 0;
+    const int wstage = c->UT == 4 ? 2 * rows * rows * (int)sizeof(float) : 0;     // cp.async weight double buffer
+    c->smem_full = smem_for(nd.C, c->TP) + scratch + wstage;
+    c->smem_val = smem_for(1, c->TP) + scratch + wstage;
     c->kern_full = pick_kernel(nd.d_in, nd.n2, true, c->UT, c->TP);
     c->kern_val = pick_kernel(nd.d_in, nd.n2, false, c->UT, c->TP);
     if (!c->kern_full || !c->kern_val) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: no kernel for this configuration");
@@ -343,12 +359,9 @@ static int configure_kernels(pinn_ctx* c) {
     CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, c->kern_full, c->threads, c->smem_full));
     CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_v, c->kern_val, c->threads, c->smem_val));
     if (occ_f < 1 || occ_v < 1) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: fused kernel does not fit on an SM");
-    if (occ_v > 8) occ_v = 8;
+    if (occ_v > 4) occ_v = 4;
     c->grid_cap_full = occ_f * c->num_sms;
     c->grid_cap_val = occ_v * c->num_sms;
-    const int ntiles_hidden = (H / 4) * (H / 4);
-    int nslot = c->threads / ntiles_hidden;
-    c->nslot = nslot < 1 ? 1 : (nslot > 8 ? 8 : nslot);
     c->kernel_id = (c->UT == 8 ? 10 : 0) + (c->TP == 16 ? 1 : 0);
     if (c->cfg.precision != PINN_PREC_FP32) {
         // tensor-core kernel for the interior set; boundary / initial points keep the FP32 kernel
@@ -364,9 +377,7 @@ static int configure_kernels(pinn_ctx* c) {
         c->tc_smem = nterms * (2 * H * 256 + HW * H * 2);
         if (c->tc_smem > max_smem)
             return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: PINN_PREC_BF16X3 needs width <= 128 (operand terms do not fit in shared memory)");
-        const int mt = (H + 127) / 128;
         c->tc_tmem_cols = (H == 256) ? 512 : 2 * H;
-        (void)mt;
         CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, c->tc_smem));
         int occ = 0;
         CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->kern_tc, c->tc_threads, c->tc_smem));
@@ -391,7 +402,10 @@ static void host_init_params(const NetDims& nd, uint64_t seed, std::vector<float
     }
 }
 
-static int launch_fused(pinn_ctx* c, bool full, const PointSet* sets, int nsets, int mode, float* y_out, float* r_out) {
+// One fused launch.  `row0` is the first partial/stash row it may use; returns the grid in *grid_out.
+static int launch_fused(pinn_ctx* c, cudaStream_t stream, bool full, const PointSet* sets, int nsets, int mode,
+                        float* y_out, float* r_out, int row0, int* grid_out) {
+    if (grid_out) *grid_out = 0;
     int total = 0;
     for (int i = 0; i < nsets; i++) total += sets[i].ntiles;
     if (total == 0) return PINN_OK;
@@ -399,7 +413,8 @@ static int launch_fused(pinn_ctx* c, bool full, const PointSet* sets, int nsets,
     a.params = c->d_params; a.paramsT = c->d_paramsT;
     a.nsets = nsets;
     for (int i = 0; i < nsets; i++) a.sets[i] = sets[i];
-    a.partial = c->d_partial; a.stash = c->d_stash; a.nslot = c->nslot; a.stash_per_cta = c->stash_per_cta;
+    a.partial = c->d_partial; a.stash = c->d_stash; a.row0 = row0; a.nsplit_cap = c->nsplit_cap;
+    a.stash_per_cta = c->stash_per_cta;
     a.mode = mode; a.y_out = y_out; a.r_out = r_out;
     const bool tc = full && c->kern_tc != nullptr;
     if (tc) {                                             // 16-point tiles on the tensor-core kernel
@@ -408,44 +423,56 @@ static int launch_fused(pinn_ctx* c, bool full, const PointSet* sets, int nsets,
     }
     const int cap = tc ? c->grid_cap_tc : (full ? c->grid_cap_full : c->grid_cap_val);
     const int grid = total < cap ? total : cap;
-    const bool timed = c->prof && full && mode == 0;
+    const bool timed = c->prof && full && mode == 0 && !c->capturing;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {
         cudaEventCreate(&e0); cudaEventCreate(&e1);
-        cudaEventRecord(e0, c->stream);
+        cudaEventRecord(e0, stream);
     }
     if (tc) {
         TcArgs ta{};
         ta.f = a; ta.wq = c->d_wq; ta.wq_term_stride = c->wq_term_stride; ta.tmem_cols = c->tc_tmem_cols;
-        c->kern_tc<<<grid, c->tc_threads, c->tc_smem, c->stream>>>(c->nd, ta);
+        c->kern_tc<<<grid, c->tc_threads, c->tc_smem, stream>>>(c->nd, ta);
     } else {
-        (full ? c->kern_full : c->kern_val)<<<grid, c->threads, full ? c->smem_full : c->smem_val, c->stream>>>(c->nd, a);
+        (full ? c->kern_full : c->kern_val)<<<grid, c->threads, full ? c->smem_full : c->smem_val, stream>>>(c->nd, a);
     }
-    if (timed) { cudaEventRecord(e1, c->stream); c->pending.emplace_back(e0, e1); }
+    if (timed) { cudaEventRecord(e1, stream); c->pending.emplace_back(e0, e1); }
     if (full) c->last_grid = grid;
-    if (mode == 0 && grid > c->rows_dirty) c->rows_dirty = grid;
-    c->launches++;
+    if (grid_out) *grid_out = grid;
+    c->step_launches++;
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
     return PINN_OK;
 }
 
+// Local part of a step: interior launch on the main stream, boundary + initial launch concurrently
+// on the auxiliary stream (disjoint partial rows), then the fixed-order reduction of all rows.
 static int run_local(pinn_ctx* c, int bump_step) {
-    PointSet s{};
-    s.x = c->d_x[0]; s.n = c->n_local[0]; s.scale = c->scale[0]; s.set = PINN_SET_INTERIOR; s.ntiles = tiles_of(s.n, c->TP);
-    int rc = launch_fused(c, true, &s, 1, 0, nullptr, nullptr);
-    if (rc) return rc;
     PointSet v[2]; int nv = 0;
     for (int k = 1; k <= 2; k++) {
         if (c->n_local[k] == 0) continue;
         v[nv].x = c->d_x[k]; v[nv].n = c->n_local[k]; v[nv].scale = c->scale[k]; v[nv].set = k;
         v[nv].ntiles = tiles_of(c->n_local[k], c->TP); nv++;
     }
-    if (nv) { rc = launch_fused(c, false, v, nv, 0, nullptr, nullptr); if (rc) return rc; }
+    if (nv) {
+        CUDA_TRY(c, "pinn_train_step", cudaEventRecord(c->ev_fork, c->stream));
+        CUDA_TRY(c, "pinn_train_step", cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    }
+    PointSet s{};
+    s.x = c->d_x[0]; s.n = c->n_local[0]; s.scale = c->scale[0]; s.set = PINN_SET_INTERIOR; s.ntiles = tiles_of(s.n, c->TP);
+    int grid_a = 0, grid_b = 0;
+    int rc = launch_fused(c, c->stream, true, &s, 1, 0, nullptr, nullptr, 0, &grid_a);
+    if (rc) return rc;
+    if (nv) {
+        const int row0 = c->rows_cap_a;                   // rows [0, rows_cap_a) belong to the interior launch
+        rc = launch_fused(c, c->stream2, false, v, nv, 0, nullptr, nullptr, row0, &grid_b);
+        if (rc) return rc;
+        CUDA_TRY(c, "pinn_train_step", cudaEventRecord(c->ev_join, c->stream2));
+        CUDA_TRY(c, "pinn_train_step", cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    }
     const int n_out = c->nd.P + 3;
-    reduce_partials_kernel<<<(n_out + 31) / 32, dim3(32, 32), 0, c->stream>>>(c->d_partial, c->rows_dirty * c->nslot, c->nd.PP,
-                                                                            n_out, c->d_gbuf, c->d_step, bump_step);
-    c->rows_dirty = 0;
-    c->launches++;
+    reduce_partials_kernel<<<(n_out + 31) / 32, dim3(32, 32), 0, c->stream>>>(
+        c->d_partial, grid_a, c->d_partial + (size_t)c->rows_cap_a * c->nd.PP, grid_b, c->nd.PP, n_out, c->d_gbuf, c->d_step, bump_step);
+    c->step_launches++;
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
     return PINN_OK;
 }
@@ -454,7 +481,7 @@ static void refresh_wq(pinn_ctx* c) {
     if (!c->d_wq) return;
     const long long n = c->wq_term_stride;
     pack_wq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->nd, c->d_params, c->d_wq, c->wq_term_stride, c->nterms);
-    c->launches++;
+    c->step_launches++;
 }
 
 static int run_allreduce(pinn_ctx* c) {
@@ -468,11 +495,62 @@ static int run_allreduce(pinn_ctx* c) {
 static int run_apply(pinn_ctx* c, int apply) {
     adam_kernel<<<(c->nd.P + 255) / 256, 256, 0, c->stream>>>(c->nd, c->adam, c->d_params, c->d_paramsT, c->d_m, c->d_v,
                                                             c->d_gbuf, c->d_step, c->d_loss, c->d_flag, apply);
-    c->launches++;
+    c->step_launches++;
     if (apply) refresh_wq(c);
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
-    if (apply) c->host_step++;
     return PINN_OK;
+}
+
+// All device work of one training step, issued on the handle's streams (directly, or under capture).
+static int issue_step(pinn_ctx* c) {
+    int rc = run_local(c, 1);
+    if (!rc) rc = run_allreduce(c);
+    if (!rc) rc = run_apply(c, 1);
+    return rc;
+}
+
+static void drop_graph(pinn_ctx* c) {
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->graph) cudaGraphDestroy(c->graph);
+    c->graph_exec = nullptr; c->graph = nullptr;
+}
+
+// One training step: replay of a captured CUDA graph (interior || boundary/initial -> reduce ->
+// all-reduce -> Adam) unless per-kernel profiling is on.  Re-captured when the point counts change.
+static int step_once(pinn_ctx* c) {
+    const bool want_graph = c->graph_ok && !c->prof;
+    if (want_graph) {
+        const uint64_t key[4] = {c->n_local[0], c->n_local[1], c->n_local[2], (uint64_t)(c->comm != nullptr)};
+        if (!c->graph_exec || memcmp(key, c->graph_key, sizeof(key)) != 0) {
+            drop_graph(c);
+            c->step_launches = 0; c->capturing = true;
+            cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+            int rc = (e == cudaSuccess) ? issue_step(c) : PINN_ERR_CUDA;
+            cudaGraph_t g = nullptr;
+            if (e == cudaSuccess) e = cudaStreamEndCapture(c->stream, &g);
+            c->capturing = false;
+            if (e == cudaSuccess && rc == PINN_OK && g) e = cudaGraphInstantiate(&c->graph_exec, g, 0);
+            if (e != cudaSuccess || rc != PINN_OK || !c->graph_exec) {
+                if (g) cudaGraphDestroy(g);
+                cudaGetLastError();
+                c->graph_exec = nullptr; c->graph_ok = false;        // fall back to direct launches for this handle
+            } else {
+                c->graph = g; memcpy(c->graph_key, key, sizeof(key));
+                c->launches_per_graph = c->step_launches;
+            }
+        }
+        if (c->graph_exec) {
+            CUDA_TRY(c, "pinn_train_step", cudaGraphLaunch(c->graph_exec, c->stream));
+            c->launches += c->launches_per_graph;
+            c->host_step++;
+            return PINN_OK;
+        }
+    }
+    c->step_launches = 0;
+    const int rc = issue_step(c);
+    c->launches += c->step_launches;
+    if (!rc) c->host_step++;
+    return rc;
 }
 
 static int read_out(pinn_ctx* c, pinn_step_out* out) {
@@ -526,6 +604,9 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
 #define TRY_C(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { c->err = std::string("pinn_create: ") + #call + " -> " + cudaGetErrorString(e_); return bail(PINN_ERR_CUDA); } } while (0)
     TRY_C(cudaSetDevice(cfg->device));
     TRY_C(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    TRY_C(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    TRY_C(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    TRY_C(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     int rc = configure_kernels(c);
     if (rc) return bail(rc);
 
@@ -545,15 +626,12 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     c->adam.inv_nb = counts[1] ? 1.0 / (double)counts[1] : 0.0;
     c->adam.inv_n0 = counts[2] ? 1.0 / (double)counts[2] : 0.0;
 
-    // grids are bounded by the tile counts, so size the per-CTA scratch by what can actually launch
-    const int tiles_f = tiles_of(c->cap[0], c->TP);
-    const int tiles_v = tiles_of(c->cap[1], c->TP) + tiles_of(c->cap[2], c->TP);
-    int gmax_f = tiles_f < c->grid_cap_full ? tiles_f : c->grid_cap_full;
-    int gmax_v = tiles_v < c->grid_cap_val ? tiles_v : c->grid_cap_val;
-    // evaluation calls (pinn_forward / pinn_residual) may use the full grid caps
-    gmax_f = c->grid_cap_full; gmax_v = c->grid_cap_val;
-    c->nrows_cta = gmax_f > gmax_v ? gmax_f : gmax_v;
-    if (c->grid_cap_tc > c->nrows_cta) c->nrows_cta = c->grid_cap_tc;
+    // partial / stash rows: [0, rows_cap_a) interior launch (FP32 or tensor-core kernel, also the
+    // evaluation calls), [rows_cap_a, rows_cap_a + rows_cap_b) the concurrent boundary/initial launch
+    c->rows_cap_a = c->grid_cap_full > c->grid_cap_tc ? c->grid_cap_full : c->grid_cap_tc;
+    if (c->grid_cap_val > c->rows_cap_a) c->rows_cap_a = c->grid_cap_val;      // pinn_forward uses the value kernel on rows A
+    c->rows_cap_b = c->grid_cap_val;
+    const size_t nrows = (size_t)c->rows_cap_a + c->rows_cap_b;
     c->stash_per_cta = (long long)nd.L * nd.C * nd.H * c->TP;   // the tensor-core kernel (16-point tiles) needs no more
     const size_t P = nd.P;
     TRY_C(cudaMalloc(&c->d_params, P * sizeof(float)));
@@ -561,8 +639,8 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     TRY_C(cudaMalloc(&c->d_m, P * sizeof(float)));
     TRY_C(cudaMalloc(&c->d_v, P * sizeof(float)));
     TRY_C(cudaMalloc(&c->d_gbuf, (size_t)nd.PP * sizeof(float)));
-    TRY_C(cudaMalloc(&c->d_partial, (size_t)c->nrows_cta * c->nslot * nd.PP * sizeof(float)));
-    TRY_C(cudaMalloc(&c->d_stash, (size_t)c->nrows_cta * c->stash_per_cta * sizeof(float)));
+    TRY_C(cudaMalloc(&c->d_partial, nrows * nd.PP * sizeof(float)));
+    TRY_C(cudaMalloc(&c->d_stash, nrows * c->stash_per_cta * sizeof(float)));
     if (c->kern_tc && nd.L >= 2) {
         c->wq_term_stride = (long long)(nd.L - 1) * nd.H * nd.H;
         TRY_C(cudaMalloc(&c->d_wq, (size_t)c->nterms * c->wq_term_stride * sizeof(__nv_bfloat16)));
@@ -574,7 +652,7 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     TRY_C(cudaMemsetAsync(c->d_m, 0, P * sizeof(float), c->stream));
     TRY_C(cudaMemsetAsync(c->d_v, 0, P * sizeof(float), c->stream));
     TRY_C(cudaMemsetAsync(c->d_gbuf, 0, (size_t)nd.PP * sizeof(float), c->stream));
-    TRY_C(cudaMemsetAsync(c->d_partial, 0, (size_t)c->nrows_cta * c->nslot * nd.PP * sizeof(float), c->stream));
+    TRY_C(cudaMemsetAsync(c->d_partial, 0, nrows * nd.PP * sizeof(float), c->stream));
     TRY_C(cudaMemsetAsync(c->d_loss, 0, 4 * sizeof(float), c->stream));
     TRY_C(cudaMemsetAsync(c->d_step, 0, sizeof(unsigned long long), c->stream));
     TRY_C(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
@@ -592,6 +670,7 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
 void pinn_destroy(pinn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
     if (c->stream) cudaStreamSynchronize(c->stream);
     drain_profile(c);
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
@@ -600,6 +679,10 @@ void pinn_destroy(pinn_ctx* c) {
     cudaFree(c->d_gbuf); cudaFree(c->d_partial); cudaFree(c->d_stash); cudaFree(c->d_loss);
     cudaFree(c->d_step); cudaFree(c->d_flag); cudaFree(c->d_wq);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    drop_graph(c);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -698,23 +781,27 @@ size_t pinn_local_count(const pinn_ctx* c, int set) { return (c && set >= 0 && s
 int pinn_step_local(pinn_ctx* c) {
     if (!c) return PINN_ERR_INVALID_ARGUMENT;
     CUDA_TRY(c, "pinn_step_local", cudaSetDevice(c->cfg.device));
-    return run_local(c, 1);
+    c->step_launches = 0;
+    const int rc = run_local(c, 1);
+    c->launches += c->step_launches;
+    return rc;
 }
 
 int pinn_step_apply(pinn_ctx* c, pinn_step_out* out) {
     if (!c) return PINN_ERR_INVALID_ARGUMENT;
     CUDA_TRY(c, "pinn_step_apply", cudaSetDevice(c->cfg.device));
+    c->step_launches = 0;
     int rc = run_apply(c, 1);
+    c->launches += c->step_launches;
     if (rc) return rc;
+    c->host_step++;
     return read_out(c, out);
 }
 
 int pinn_train_step(pinn_ctx* c, pinn_step_out* out) {
     if (!c) return PINN_ERR_INVALID_ARGUMENT;
     CUDA_TRY(c, "pinn_train_step", cudaSetDevice(c->cfg.device));
-    int rc = run_local(c, 1);
-    if (!rc) rc = run_allreduce(c);
-    if (!rc) rc = run_apply(c, 1);
+    int rc = step_once(c);
     if (!rc) rc = read_out(c, out);
     return rc;
 }
@@ -723,9 +810,7 @@ int pinn_train_steps(pinn_ctx* c, int k, pinn_step_out* out) {
     if (!c || k < 1) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_train_steps: k must be >= 1");
     CUDA_TRY(c, "pinn_train_steps", cudaSetDevice(c->cfg.device));
     for (int s = 0; s < k; s++) {
-        int rc = run_local(c, 1);
-        if (!rc) rc = run_allreduce(c);
-        if (!rc) rc = run_apply(c, 1);
+        const int rc = step_once(c);
         if (rc) return rc;
     }
     return read_out(c, out);
@@ -741,9 +826,11 @@ int pinn_train_step_host(pinn_ctx* c, const float* x_interior, size_t n, pinn_st
 int pinn_loss_grad(pinn_ctx* c, pinn_step_out* out) {
     if (!c) return PINN_ERR_INVALID_ARGUMENT;
     CUDA_TRY(c, "pinn_loss_grad", cudaSetDevice(c->cfg.device));
+    c->step_launches = 0;
     int rc = run_local(c, 0);
     if (!rc) rc = run_allreduce(c);
     if (!rc) rc = run_apply(c, 0);
+    c->launches += c->step_launches;
     if (!rc) rc = read_out(c, out);
     return rc;
 }
@@ -761,7 +848,9 @@ static int eval_common(pinn_ctx* c, const char* fn, bool full, const float* x, f
     CUDA_TRY(c, fn, cudaMemcpyAsync(dx, x, n * nd.d_in * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     PointSet s{};
     s.x = dx; s.n = n; s.scale = 0.0f; s.set = full ? PINN_SET_INTERIOR : PINN_SET_BOUNDARY; s.ntiles = tiles_of(n, c->TP);
-    int rc = launch_fused(c, full, &s, 1, 1, dy, dr);
+    c->step_launches = 0;
+    int rc = launch_fused(c, c->stream, full, &s, 1, 1, dy, dr, 0, nullptr);
+    c->launches += c->step_launches;
     if (rc) return rc;
     if (y) CUDA_TRY(c, fn, cudaMemcpyAsync(y, dy, n * nd.d_out * nc * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     if (r && full) CUDA_TRY(c, fn, cudaMemcpyAsync(r, dr, n * nd.n_res * sizeof(float), cudaMemcpyDeviceToHost, c->stream));

@@ -35,9 +35,10 @@ struct FusedArgs {
     const float* paramsT;       // same offsets, W^T per layer ([fan_out, fan_in])
     PointSet sets[2];
     int nsets;
-    float* partial;             // [grid][nslot][PP]
-    float* stash;               // [grid][stash_per_cta]
-    int nslot;
+    float* partial;             // [rows][PP]: one row per CTA of every launch of the step
+    float* stash;               // [rows][stash_per_cta]
+    int row0;                   // first partial / stash row of this launch (launches of one step run concurrently)
+    int nsplit_cap;             // > 1: dW micro-tiles may split the tile columns, partials meet in smem scratch
     long long stash_per_cta;    // floats
     int mode;                   // 0 = train (loss + gradients), 1 = evaluate (y, r out)
     float* y_out;               // eval: [n, d_out, NC]
@@ -45,7 +46,8 @@ struct FusedArgs {
 };
 
 // acc[c][u] = sum_k bufIn[k][c*TP+p] * Wg[k*N + j0+u]      (k ascending, zero-initialised)
-template <int NC, int UT, int TP>
+// WS = true: Wg is a shared-memory copy staged by cp.async (narrow nets); false: global, read-only path.
+template <int NC, int UT, int TP, bool WS = false>
 __device__ __forceinline__ void gemm_rows(const float* __restrict__ bufIn, int LD,
                                           const float* __restrict__ Wg, int K, int N, int j0, int p,
                                           float (&acc)[NC][UT]) {
@@ -64,7 +66,8 @@ __device__ __forceinline__ void gemm_rows(const float* __restrict__ bufIn, int L
             for (int c = 0; c < NC; c++) a[c] = a_ptr[k * LD + c * TP];
             #pragma unroll
             for (int q = 0; q < UT / 4; q++) {
-                float4 t = __ldg(reinterpret_cast<const float4*>(w_ptr + (size_t)k * N) + q);
+                float4 t = WS ? *(reinterpret_cast<const float4*>(w_ptr + (size_t)k * N) + q)
+                              : __ldg(reinterpret_cast<const float4*>(w_ptr + (size_t)k * N) + q);
                 w[4 * q + 0] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
             }
             #pragma unroll
@@ -79,7 +82,7 @@ __device__ __forceinline__ void gemm_rows(const float* __restrict__ bufIn, int L
             for (int c = 0; c < NC; c++) a[c] = a_ptr[k * LD + c * TP];
             #pragma unroll
             for (int u = 0; u < UT; u++) {
-                float w = (j0 + u < N) ? __ldg(Wg + (size_t)k * N + j0 + u) : 0.0f;
+                float w = (j0 + u < N) ? (WS ? Wg[(size_t)k * N + j0 + u] : __ldg(Wg + (size_t)k * N + j0 + u)) : 0.0f;
                 #pragma unroll
                 for (int c = 0; c < NC; c++) acc[c][u] = fmaf(a[c], w, acc[c][u]);
             }
@@ -87,18 +90,29 @@ __device__ __forceinline__ void gemm_rows(const float* __restrict__ bufIn, int L
     }
 }
 
-// part[k*fo + j] += sum_m bufA[k][m] * bufZ[j][m]  over the tile's M = NC*TP columns.
-// 4x4 register micro-tiles with strided row ownership; when there are fewer micro-tiles than
-// threads the column range is split over `nslot` partial rows (summed later in fixed order).
+// Gradient accumulation into this CTA's private partial row: every element has exactly one owning
+// thread, so a fire-and-forget reduction (RED.ADD, no return value => no stall on the L2 round trip)
+// is still applied in program order per address => bit-reproducible.
+__device__ __forceinline__ void red_add(float* addr, float v) { atomicAdd(addr, v); }
+
+__device__ __forceinline__ int dw_nsplit(int ntiles, int nsplit_cap, int M4) {
+    int nsplit = (int)blockDim.x / ntiles;
+    nsplit = nsplit < 1 ? 1 : (nsplit > nsplit_cap ? nsplit_cap : nsplit);
+    return nsplit > M4 ? M4 : nsplit;
+}
+
+// dW[k][j] = sum_m bufA[k][m] * bufZ[j][m] over the tile's M = NC*TP columns: 4x4 register
+// micro-tiles with strided row ownership.  With fewer micro-tiles than threads the columns are split
+// over `nsplit` thread groups whose partial tiles go to `scratch` (summed by dw_flush after the next
+// barrier); otherwise the tile is added straight into the partial row.
 template <int NC, int TP>
-__device__ __forceinline__ void dw_tile(const float* __restrict__ bufA, const float* __restrict__ bufZ,
-                                        int LD, int fi, int fo, float* __restrict__ part, int PP, int nslot) {
+__device__ __forceinline__ void dw_compute(const float* __restrict__ bufA, const float* __restrict__ bufZ,
+                                           int LD, int fi, int fo, float* __restrict__ part,
+                                           float* __restrict__ scratch, int nsplit_cap) {
     constexpr int M4 = NC * TP / 4;
     const int NKB = (fi + 3) >> 2, NJB = (fo + 3) >> 2, ntiles = NKB * NJB;
     const int nthreads = blockDim.x;
-    int nsplit = nthreads / ntiles;
-    nsplit = nsplit < 1 ? 1 : (nsplit > nslot ? nslot : nsplit);
-    if (nsplit > M4) nsplit = M4;
+    const int nsplit = dw_nsplit(ntiles, nsplit_cap, M4);
     for (int w = threadIdx.x; w < ntiles * nsplit; w += nthreads) {
         const int tile = w % ntiles, sp = w / ntiles;
         const int kb = tile / NJB, jb = tile - kb * NJB;
@@ -132,21 +146,65 @@ __device__ __forceinline__ void dw_tile(const float* __restrict__ bufA, const fl
                     acc[i][j] = fmaf(a[i].w, z[j].w, acc[i][j]);
                 }
         }
-        float* dst = part + (size_t)sp * PP;
-        #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int k = kb + i * NKB;
+        if (nsplit == 1) {
             #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int jj = jb + j * NJB;
-                if (k < fi && jj < fo) dst[k * fo + jj] += acc[i][j];
+            for (int i = 0; i < 4; i++) {
+                const int k = kb + i * NKB;
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int jj = jb + j * NJB;
+                    if (k < fi && jj < fo) red_add(part + k * fo + jj, acc[i][j]);
+                }
             }
+        } else {
+            float4* dst = reinterpret_cast<float4*>(scratch + (size_t)w * 16);
+            #pragma unroll
+            for (int i = 0; i < 4; i++) dst[i] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         }
     }
 }
 
-template <int DIN, int N2, bool FULL, int UT, int TP>
-__global__ void __launch_bounds__(512)
+// Second half of a split dW: after a barrier, element e of micro-tile `tile` is summed over the
+// splits in fixed order by one thread and added to the partial row.
+template <int NC, int TP>
+__device__ __forceinline__ void dw_flush(int fi, int fo, float* __restrict__ part,
+                                         const float* __restrict__ scratch, int nsplit_cap) {
+    constexpr int M4 = NC * TP / 4;
+    const int NKB = (fi + 3) >> 2, NJB = (fo + 3) >> 2, ntiles = NKB * NJB;
+    const int nsplit = dw_nsplit(ntiles, nsplit_cap, M4);
+    if (nsplit == 1) return;
+    for (int idx = threadIdx.x; idx < ntiles * 16; idx += blockDim.x) {
+        const int tile = idx >> 4, e = idx & 15, i = e >> 2, j = e & 3;
+        const int kb = tile / NJB, jb = tile - kb * NJB;
+        const int k = kb + i * NKB, jj = jb + j * NJB;
+        if (k < fi && jj < fo) {
+            float sum = 0.0f;
+            for (int sp = 0; sp < nsplit; sp++) sum += scratch[(size_t)(sp * ntiles + tile) * 16 + e];
+            red_add(part + k * fo + jj, sum);
+        }
+    }
+}
+
+// ---- weight staging for narrow nets: one contraction ahead, cp.async (LDGSTS) double buffer ----
+// Schedule of the matrices a tile consumes, in order: W_1..W_L, W_{L+1}, W^T_{L+1}, W^T_L..W^T_2.
+__device__ __forceinline__ const float* wsched(const NetDims& nd, const FusedArgs& args, int q, int* nfloat) {
+    const int L = nd.L;
+    int l; const float* base;
+    if (q <= L) { l = q + 1; base = args.params; }                // forward: W_{q+1}
+    else { l = 2 * L + 2 - q; base = args.paramsT; }              // reverse: W^T_{L+1}, W^T_L, ...
+    *nfloat = nd.fan_in(l) * nd.fan_out(l);
+    return base + nd.offW[l];
+}
+__device__ __forceinline__ void wstage_issue(float* dst, const float* __restrict__ src, int nfloat) {
+    const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
+    for (int i = threadIdx.x * 4; i < nfloat; i += blockDim.x * 4)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + i * 4), "l"(src + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void wstage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int DIN, int N2, bool FULL, int UT, int TP, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 fused_step_fp32(const NetDims nd, const FusedArgs args) {
     constexpr int NC = FULL ? 1 + DIN + N2 : 1;
     constexpr int LD = NC * TP + 4;
@@ -155,11 +213,30 @@ fused_step_fp32(const NetDims nd, const FusedArgs args) {
     const int rows = (H + 3) & ~3;
     float* bufA = smem;
     float* bufZ = smem + (size_t)rows * LD;
+    float* scratch = bufZ + (size_t)rows * LD;          // [blockDim.x][16] when nsplit_cap > 1
+    constexpr bool WS = (UT == 4);                      // narrow nets: weights staged in smem, one contraction ahead
+    float* wbuf = scratch + (args.nsplit_cap > 1 ? (size_t)blockDim.x * 16 : 0);   // [2][rows*rows] when WS
+    const int wslot = rows * rows;
+    const int nq = 2 * L + 1;                           // matrices per tile: q = 0 .. 2L
+    int q = 0;                                          // next matrix to consume (block-uniform)
+    // consume(): wait for matrix q, make it visible, prefetch matrix q+1 (next tile wraps to W_1)
+    auto w_consume = [&]() -> const float* {
+        if constexpr (!WS) return nullptr;
+        wstage_wait();
+        __syncthreads();                                // copy of q visible to all; buffer (q+1)&1 no longer read
+        int nf; const int qn = (q + 1 > nq - 1) ? 0 : q + 1;
+        const float* src = wsched(nd, args, qn, &nf);
+        wstage_issue(wbuf + ((q + 1) & 1) * wslot, src, nf);
+        const float* cur = wbuf + (q & 1) * wslot;
+        q++;
+        return cur;
+    };
+    if constexpr (WS) { int nf; const float* src = wsched(nd, args, 0, &nf); wstage_issue(wbuf, src, nf); }
 
     const int tid = threadIdx.x;
     const int p = tid % TP, g = tid / TP, j0 = g * UT;
-    float* stash = args.stash + (size_t)blockIdx.x * args.stash_per_cta;
-    float* part = args.partial + (size_t)blockIdx.x * args.nslot * nd.PP;
+    float* stash = args.stash + (size_t)(args.row0 + blockIdx.x) * args.stash_per_cta;
+    float* part = args.partial + (size_t)(args.row0 + blockIdx.x) * nd.PP;
     const int total_tiles = args.sets[0].ntiles + (args.nsets > 1 ? args.sets[1].ntiles : 0);
     const size_t lstride = (size_t)NC * H * TP;          // stash floats per layer
 
@@ -188,7 +265,8 @@ fused_step_fp32(const NetDims nd, const FusedArgs args) {
 
         // ---------------------------------- forward ----------------------------------
         for (int l = 1; l <= L; l++) {
-            gemm_rows<NC, UT, TP>(bufA, LD, args.params + nd.offW[l], l == 1 ? DIN : H, H, j0, p, acc);
+            if constexpr (WS) { const float* wl = w_consume(); gemm_rows<NC, UT, TP, true>(bufA, LD, wl, l == 1 ? DIN : H, H, j0, p, acc); }
+            else gemm_rows<NC, UT, TP>(bufA, LD, args.params + nd.offW[l], l == 1 ? DIN : H, H, j0, p, acc);
             float* st = stash + (size_t)(l - 1) * lstride + (size_t)j0 * TP + p;
             #pragma unroll
             for (int u = 0; u < UT; u++) {
@@ -219,7 +297,8 @@ fused_step_fp32(const NetDims nd, const FusedArgs args) {
         }
 
         // ---- linear output layer, residual / target, loss seeds ----
-        gemm_rows<NC, UT, TP>(bufA, LD, args.params + nd.offW[L + 1], H, nd.d_out, j0, p, acc);
+        if constexpr (WS) { const float* wl = w_consume(); gemm_rows<NC, UT, TP, true>(bufA, LD, wl, H, nd.d_out, j0, p, acc); }
+        else gemm_rows<NC, UT, TP>(bufA, LD, args.params + nd.offW[L + 1], H, nd.d_out, j0, p, acc);
         if (g == 0) {
             float y[3][NC], ybar[3][NC], r[3] = {0.0f, 0.0f, 0.0f};
             #pragma unroll
@@ -264,19 +343,24 @@ fused_step_fp32(const NetDims nd, const FusedArgs args) {
                     #pragma unroll
                     for (int c = 0; c < NC; c++) bufZ[o * LD + c * TP + p] = ybar[o][c];
                     const float sb = lane_group_sum<TP>(ybar[o][0]);
-                    if (p == 0) part[nd.offB[L + 1] + o] += sb;
+                    if (p == 0) red_add(part + nd.offB[L + 1] + o, sb);
                 }
                 const float sl = lane_group_sum<TP>(ss);
-                if (p == 0) part[nd.P + ps.set] += sl;
+                if (p == 0) red_add(part + nd.P + ps.set, sl);
             }
         }
-        if (args.mode == 1) continue;
+        if (args.mode == 1) {                           // evaluation: skip the reverse matrices of the schedule
+            if constexpr (WS) { wstage_wait(); __syncthreads(); int nf; const float* src = wsched(nd, args, 0, &nf); wstage_issue(wbuf, src, nf); q = 0; }
+            continue;
+        }
         __syncthreads();
 
         // ---------------------------------- reverse ----------------------------------
-        dw_tile<NC, TP>(bufA, bufZ, LD, H, nd.d_out, part + nd.offW[L + 1], nd.PP, args.nslot);
-        gemm_rows<NC, UT, TP>(bufZ, LD, args.paramsT + nd.offW[L + 1], nd.d_out, H, j0, p, acc);
+        dw_compute<NC, TP>(bufA, bufZ, LD, H, nd.d_out, part + nd.offW[L + 1], scratch, args.nsplit_cap);
+        if constexpr (WS) { const float* wl = w_consume(); gemm_rows<NC, UT, TP, true>(bufZ, LD, wl, nd.d_out, H, j0, p, acc); }
+        else gemm_rows<NC, UT, TP>(bufZ, LD, args.paramsT + nd.offW[L + 1], nd.d_out, H, j0, p, acc);
         __syncthreads();
+        dw_flush<NC, TP>(H, nd.d_out, part + nd.offW[L + 1], scratch, args.nsplit_cap);
 
         for (int l = L; l >= 1; l--) {
             // elementwise adjoint of the tanh layer: acc = Abar_l  →  Zbar_l into bufZ
@@ -306,7 +390,7 @@ fused_step_fp32(const NetDims nd, const FusedArgs args) {
                 }
                 zrow[0] = zb0;
                 const float sb = lane_group_sum<TP>(zb0);
-                if (p == 0) part[nd.offB[l] + j0 + u] += sb;
+                if (p == 0) red_add(part + nd.offB[l] + j0 + u, sb);
             }
             // A_{l-1} (the dW operand) back into bufA: recomputed from the stash, or the inputs
             if (l > 1) {
@@ -337,11 +421,17 @@ fused_step_fp32(const NetDims nd, const FusedArgs args) {
                         bufA[k * LD + c * TP + p] = (c == 0) ? x[k] : ((c == 1 + k) ? 1.0f : 0.0f);
             }
             __syncthreads();
-            dw_tile<NC, TP>(bufA, bufZ, LD, l == 1 ? DIN : H, H, part + nd.offW[l], nd.PP, args.nslot);
-            if (l > 1) gemm_rows<NC, UT, TP>(bufZ, LD, args.paramsT + nd.offW[l], H, H, j0, p, acc);
+            dw_compute<NC, TP>(bufA, bufZ, LD, l == 1 ? DIN : H, H, part + nd.offW[l], scratch, args.nsplit_cap);
+            if (l > 1) {
+                if constexpr (WS) { const float* wl = w_consume(); gemm_rows<NC, UT, TP, true>(bufZ, LD, wl, H, H, j0, p, acc); }
+                else gemm_rows<NC, UT, TP>(bufZ, LD, args.paramsT + nd.offW[l], H, H, j0, p, acc);
+            }
             __syncthreads();
+            dw_flush<NC, TP>(l == 1 ? DIN : H, H, part + nd.offW[l], scratch, args.nsplit_cap);
         }
+        q = 0;                                          // the last prefetch of the tile was W_1 of the next one
     }
+    if constexpr (WS) wstage_wait();
 }
 
 }  // namespace pinn

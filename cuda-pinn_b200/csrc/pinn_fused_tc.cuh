@@ -61,8 +61,8 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int p = tid % TP, g = tid / TP, j0 = g * UT;
     const int nwarps = blockDim.x >> 5, lg = warp & 3, wsub = warp >> 2, nsub = nwarps >> 2;
-    float* stash = args.stash + (size_t)blockIdx.x * args.stash_per_cta;
-    float* part = args.partial + (size_t)blockIdx.x * args.nslot * nd.PP;
+    float* stash = args.stash + (size_t)(args.row0 + blockIdx.x) * args.stash_per_cta;
+    float* part = args.partial + (size_t)(args.row0 + blockIdx.x) * nd.PP;
     const size_t lstride = (size_t)NC * H * TP;
 
     if (warp == 0) umma::tmem_alloc(&tmem_slot, (uint32_t)ta.tmem_cols);
@@ -290,10 +290,10 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                     #pragma unroll
                     for (int c = 0; c < NC; c++) ybuf[(o * NC + c) * TP + p] = ybar[o][c];
                     const float sb = lane_group_sum<TP>(ybar[o][0]);
-                    if (p == 0 && o < nd.d_out) part[nd.offB[L + 1] + o] += sb;
+                    if (p == 0 && o < nd.d_out) red_add(part + nd.offB[L + 1] + o, sb);
                 }
                 const float sl = lane_group_sum<TP>(ss);
-                if (p == 0) part[nd.P + ps.set] += sl;
+                if (p == 0) red_add(part + nd.P + ps.set, sl);
             }
         }
         __syncthreads();
@@ -314,7 +314,7 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                     #pragma unroll
                     for (int c = 0; c < NC; c++) s = fmaf(acc[c][u], yb[o][c], s);
                     s = lane_group_sum<TP>(s);
-                    if (p == 0 && o < nd.d_out) part[nd.offW[L + 1] + (j0 + u) * nd.d_out + o] += s;
+                    if (p == 0 && o < nd.d_out) red_add(part + nd.offW[L + 1] + (j0 + u) * nd.d_out + o, s);
                 }
             #pragma unroll
             for (int u = 0; u < UT; u++)
@@ -354,7 +354,7 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                 }
                 acc[0][u] = zb0;
                 const float sb = lane_group_sum<TP>(zb0);
-                if (p == 0) part[nd.offB[l] + j0 + u] += sb;
+                if (p == 0) red_add(part + nd.offB[l] + j0 + u, sb);
             }
             if (l == 1) {
                 // dW_1[k][j] = sum_p ( x_k * zbar_0 + zbar_{1+k} )   (inputs: value x, unit tangents)
@@ -363,7 +363,7 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                     #pragma unroll
                     for (int k = 0; k < DIN; k++) {
                         const float s = lane_group_sum<TP>(fmaf(x[k], acc[0][u], acc[1 + k][u]));
-                        if (p == 0) part[nd.offW[1] + k * H + j0 + u] += s;
+                        if (p == 0) red_add(part + nd.offW[1] + k * H + j0 + u, s);
                     }
                 break;
             }
@@ -413,12 +413,11 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                             umma::tmem_ld16_nowait(tmem + ((uint32_t)(lg * 32) << 16) + tt * H + c, r);
                             umma::tmem_ld_wait();
                             float4* d4 = reinterpret_cast<float4*>(dst + (size_t)k * H + c);
-                            #pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                float4 v = d4[q];
-                                v.x += __uint_as_float(r[4 * q + 0]); v.y += __uint_as_float(r[4 * q + 1]);
-                                v.z += __uint_as_float(r[4 * q + 2]); v.w += __uint_as_float(r[4 * q + 3]);
-                                d4[q] = v;
+                            if (k < H) {
+                                #pragma unroll
+                                for (int q = 0; q < 4; q++)     // 16-byte vector reduction, single owner per element
+                                    atomicAdd(d4 + q, make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
+                                                                  __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
                             }
                         }
                     }
