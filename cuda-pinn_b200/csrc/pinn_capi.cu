@@ -38,20 +38,27 @@ __global__ void __launch_bounds__(1024)
 reduce_partials_kernel(float* __restrict__ part_a, int rows_a, float* __restrict__ part_b, int rows_b, int PP, int n_out,
                        float* __restrict__ gbuf, unsigned long long* step, int bump) {
     __shared__ float part[32][33];
+    constexpr int RU = 8;                                // independent loads in flight per thread
     const int col = blockIdx.x * 32 + threadIdx.x;
     if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && bump) *step += 1ULL;
     float s = 0.0f;
     if (col < n_out) {
-        for (int r = threadIdx.y; r < rows_a; r += 32) {
-            const size_t idx = (size_t)r * PP + col;
-            s += part_a[idx];
-            part_a[idx] = 0.0f;
-        }
-        for (int r = threadIdx.y; r < rows_b; r += 32) {
-            const size_t idx = (size_t)r * PP + col;
-            s += part_b[idx];
-            part_b[idx] = 0.0f;
-        }
+        auto sum_rows = [&](const float* __restrict__ base, int rows) {
+            for (int r0 = threadIdx.y; r0 < rows; r0 += 32 * RU) {
+                float v[RU];
+                #pragma unroll
+                for (int u = 0; u < RU; u++) {
+                    const int r = r0 + 32 * u;
+                    v[u] = (r < rows) ? __ldcg(base + (size_t)r * PP + col) : 0.0f;
+                }
+                #pragma unroll
+                for (int u = 0; u < RU; u++) s += v[u];  // rows in increasing order: fixed summation order
+            }
+        };
+        sum_rows(part_a, rows_a);
+        sum_rows(part_b, rows_b);
+        for (int r = threadIdx.y; r < rows_a; r += 32) part_a[(size_t)r * PP + col] = 0.0f;
+        for (int r = threadIdx.y; r < rows_b; r += 32) part_b[(size_t)r * PP + col] = 0.0f;
     }
     part[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
@@ -313,7 +320,12 @@ static fused_fn pick_ut_tp(int UT, int TP) {
     if (UT == 8 && TP == 16) return fused_step_fp32<DIN, N2, FULL, 8, 16, 512, 1>;
     return nullptr;
 }
-static fused_fn pick_kernel(int d_in, int n2, bool full, int UT, int TP) {
+static fused_fn pick_kernel(int d_in, int n2, bool full, int UT, int TP, int H) {
+    // width-specialised variants of the headline network (2 -> [20 x L] -> 1, BASELINE C1 / C2)
+    if (H == 20 && UT == 4 && TP == 32 && d_in == 2) {
+        if (full && n2 == 1) return fused_step_fp32<2, 1, true, 4, 32, 160, 6, 20>;
+        if (!full) return fused_step_fp32<2, 0, false, 4, 32, 160, 6, 20>;
+    }
     if (full) {
         if (d_in == 2 && n2 == 1) return pick_ut_tp<2, 1, true>(UT, TP);
         if (d_in == 2 && n2 == 2) return pick_ut_tp<2, 2, true>(UT, TP);
@@ -350,8 +362,8 @@ static int configure_kernels(pinn_ctx* c) {
     const int wstage = c->UT == 4 ? 2 * rows * rows * (int)sizeof(float) : 0;     // cp.async weight double buffer
     c->smem_full = smem_for(nd.C, c->TP) + scratch + wstage;
     c->smem_val = smem_for(1, c->TP) + scratch + wstage;
-    c->kern_full = pick_kernel(nd.d_in, nd.n2, true, c->UT, c->TP);
-    c->kern_val = pick_kernel(nd.d_in, nd.n2, false, c->UT, c->TP);
+    c->kern_full = pick_kernel(nd.d_in, nd.n2, true, c->UT, c->TP, H);
+    c->kern_val = pick_kernel(nd.d_in, nd.n2, false, c->UT, c->TP, H);
     if (!c->kern_full || !c->kern_val) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: no kernel for this configuration");
     CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_full, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_full));
     CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_val, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_val));

@@ -47,7 +47,7 @@ struct FusedArgs {
 
 // acc[c][u] = sum_k bufIn[k][c*TP+p] * Wg[k*N + j0+u]      (k ascending, zero-initialised)
 // WS = true: Wg is a shared-memory copy staged by cp.async (narrow nets); false: global, read-only path.
-template <int NC, int UT, int TP, bool WS = false>
+template <int NC, int UT, int TP, bool WS = false, int KU = 2>
 __device__ __forceinline__ void gemm_rows(const float* __restrict__ bufIn, int LD,
                                           const float* __restrict__ Wg, int K, int N, int j0, int p,
                                           float (&acc)[NC][UT]) {
@@ -59,7 +59,7 @@ __device__ __forceinline__ void gemm_rows(const float* __restrict__ bufIn, int L
     const float* a_ptr = bufIn + p;
     if ((j0 + UT <= N) && ((N & 3) == 0)) {
         const float* w_ptr = Wg + j0;
-        #pragma unroll 2
+        #pragma unroll KU
         for (int k = 0; k < K; k++) {
             float a[NC], w[UT];
             #pragma unroll
@@ -95,8 +95,8 @@ __device__ __forceinline__ void gemm_rows(const float* __restrict__ bufIn, int L
 // is still applied in program order per address => bit-reproducible.
 __device__ __forceinline__ void red_add(float* addr, float v) { atomicAdd(addr, v); }
 
-__device__ __forceinline__ int dw_nsplit(int ntiles, int nsplit_cap, int M4) {
-    int nsplit = (int)blockDim.x / ntiles;
+__device__ __forceinline__ int dw_nsplit(int ntiles, int nsplit_cap, int M4, int nthreads) {
+    int nsplit = nthreads / ntiles;
     nsplit = nsplit < 1 ? 1 : (nsplit > nsplit_cap ? nsplit_cap : nsplit);
     return nsplit > M4 ? M4 : nsplit;
 }
@@ -108,11 +108,10 @@ __device__ __forceinline__ int dw_nsplit(int ntiles, int nsplit_cap, int M4) {
 template <int NC, int TP>
 __device__ __forceinline__ void dw_compute(const float* __restrict__ bufA, const float* __restrict__ bufZ,
                                            int LD, int fi, int fo, float* __restrict__ part,
-                                           float* __restrict__ scratch, int nsplit_cap) {
+                                           float* __restrict__ scratch, int nsplit_cap, int nthreads) {
     constexpr int M4 = NC * TP / 4;
     const int NKB = (fi + 3) >> 2, NJB = (fo + 3) >> 2, ntiles = NKB * NJB;
-    const int nthreads = blockDim.x;
-    const int nsplit = dw_nsplit(ntiles, nsplit_cap, M4);
+    const int nsplit = dw_nsplit(ntiles, nsplit_cap, M4, nthreads);
     for (int w = threadIdx.x; w < ntiles * nsplit; w += nthreads) {
         const int tile = w % ntiles, sp = w / ntiles;
         const int kb = tile / NJB, jb = tile - kb * NJB;
@@ -168,12 +167,12 @@ __device__ __forceinline__ void dw_compute(const float* __restrict__ bufA, const
 // splits in fixed order by one thread and added to the partial row.
 template <int NC, int TP>
 __device__ __forceinline__ void dw_flush(int fi, int fo, float* __restrict__ part,
-                                         const float* __restrict__ scratch, int nsplit_cap) {
+                                         const float* __restrict__ scratch, int nsplit_cap, int nthreads) {
     constexpr int M4 = NC * TP / 4;
     const int NKB = (fi + 3) >> 2, NJB = (fo + 3) >> 2, ntiles = NKB * NJB;
-    const int nsplit = dw_nsplit(ntiles, nsplit_cap, M4);
+    const int nsplit = dw_nsplit(ntiles, nsplit_cap, M4, nthreads);
     if (nsplit == 1) return;
-    for (int idx = threadIdx.x; idx < ntiles * 16; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < ntiles * 16; idx += nthreads) {
         const int tile = idx >> 4, e = idx & 15, i = e >> 2, j = e & 3;
         const int kb = tile / NJB, jb = tile - kb * NJB;
         const int k = kb + i * NKB, jj = jb + j * NJB;
@@ -195,27 +194,32 @@ __device__ __forceinline__ const float* wsched(const NetDims& nd, const FusedArg
     *nfloat = nd.fan_in(l) * nd.fan_out(l);
     return base + nd.offW[l];
 }
-__device__ __forceinline__ void wstage_issue(float* dst, const float* __restrict__ src, int nfloat) {
+__device__ __forceinline__ void wstage_issue(float* dst, const float* __restrict__ src, int nfloat, int nthreads) {
     const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
-    for (int i = threadIdx.x * 4; i < nfloat; i += blockDim.x * 4)
+    for (int i = threadIdx.x * 4; i < nfloat; i += nthreads * 4)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + i * 4), "l"(src + i) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void wstage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int DIN, int N2, bool FULL, int UT, int TP, int MAXT, int MINB>
+// HT > 0 fixes the hidden width at compile time (contraction loops fully unrolled, offsets become
+// immediates, no runtime integer division in the dW helpers); HT = 0 reads it from NetDims.
+template <int DIN, int N2, bool FULL, int UT, int TP, int MAXT, int MINB, int HT = 0>
 __global__ void __launch_bounds__(MAXT, MINB)
 fused_step_fp32(const NetDims nd, const FusedArgs args) {
     constexpr int NC = FULL ? 1 + DIN + N2 : 1;
     constexpr int LD = NC * TP + 4;
     extern __shared__ __align__(16) float smem[];
-    const int H = nd.H, L = nd.L;
+    const int H = HT > 0 ? HT : nd.H, L = nd.L;
+    const int NTHR = HT > 0 ? TP * (HT / UT) : (int)blockDim.x;
+    const int nsplit_cap = HT > 0 ? 8 : args.nsplit_cap;     // specialised narrow variants always carry the scratch
     const int rows = (H + 3) & ~3;
     float* bufA = smem;
     float* bufZ = smem + (size_t)rows * LD;
     float* scratch = bufZ + (size_t)rows * LD;          // [blockDim.x][16] when nsplit_cap > 1
-    constexpr bool WS = (UT == 4);                      // narrow nets: weights staged in smem, one contraction ahead
-    float* wbuf = scratch + (args.nsplit_cap > 1 ? (size_t)blockDim.x * 16 : 0);   // [2][rows*rows] when WS
+    constexpr bool WS = (UT == 4);
+    constexpr int KU = HT > 0 ? (HT % 5 == 0 ? 5 : 4) : 2;   // unroll of the contraction loops                      // narrow nets: weights staged in smem, one contraction ahead
+    float* wbuf = scratch + (nsplit_cap > 1 ? (size_t)NTHR * 16 : 0);   // [2][rows*rows] when WS
     const int wslot = rows * rows;
     const int nq = 2 * L + 1;                           // matrices per tile: q = 0 .. 2L
     int q = 0;                                          // next matrix to consume (block-uniform)
@@ -226,12 +230,12 @@ fused_step_fp32(const NetDims nd, const FusedArgs args) {
         __syncthreads();                                // copy of q visible to all; buffer (q+1)&1 no longer read
         int nf; const int qn = (q + 1 > nq - 1) ? 0 : q + 1;
         const float* src = wsched(nd, args, qn, &nf);
-        wstage_issue(wbuf + ((q + 1) & 1) * wslot, src, nf);
+        wstage_issue(wbuf + ((q + 1) & 1) * wslot, src, nf, NTHR);
         const float* cur = wbuf + (q & 1) * wslot;
         q++;
         return cur;
     };
-    if constexpr (WS) { int nf; const float* src = wsched(nd, args, 0, &nf); wstage_issue(wbuf, src, nf); }
+    if constexpr (WS) { int nf; const float* src = wsched(nd, args, 0, &nf); wstage_issue(wbuf, src, nf, NTHR); }
 
     const int tid = threadIdx.x;
     const int p = tid % TP, g = tid / TP, j0 = g * UT;
@@ -265,7 +269,7 @@ fused_step_fp32(const NetDims nd, const FusedArgs args) {
 
         // ---------------------------------- forward ----------------------------------
         for (int l = 1; l <= L; l++) {
-            if constexpr (WS) { const float* wl = w_consume(); gemm_rows<NC, UT, TP, true>(bufA, LD, wl, l == 1 ? DIN : H, H, j0, p, acc); }
+            if constexpr (WS) { const float* wl = w_consume(); gemm_rows<NC, UT, TP, true, KU>(bufA, LD, wl, l == 1 ? DIN : H, H, j0, p, acc); }
             else gemm_rows<NC, UT, TP>(bufA, LD, args.params + nd.offW[l], l == 1 ? DIN : H, H, j0, p, acc);
             float* st = stash + (size_t)(l - 1) * lstride + (size_t)j0 * TP + p;
             #pragma unroll
@@ -297,7 +301,7 @@ fused_step_fp32(const NetDims nd, const FusedArgs args) {
         }
 
         // ---- linear output layer, residual / target, loss seeds ----
-        if constexpr (WS) { const float* wl = w_consume(); gemm_rows<NC, UT, TP, true>(bufA, LD, wl, H, nd.d_out, j0, p, acc); }
+        if constexpr (WS) { const float* wl = w_consume(); gemm_rows<NC, UT, TP, true, KU>(bufA, LD, wl, H, nd.d_out, j0, p, acc); }
         else gemm_rows<NC, UT, TP>(bufA, LD, args.params + nd.offW[L + 1], H, nd.d_out, j0, p, acc);
         if (g == 0) {
             float y[3][NC], ybar[3][NC], r[3] = {0.0f, 0.0f, 0.0f};
@@ -350,17 +354,17 @@ fused_step_fp32(const NetDims nd, const FusedArgs args) {
             }
         }
         if (args.mode == 1) {                           // evaluation: skip the reverse matrices of the schedule
-            if constexpr (WS) { wstage_wait(); __syncthreads(); int nf; const float* src = wsched(nd, args, 0, &nf); wstage_issue(wbuf, src, nf); q = 0; }
+            if constexpr (WS) { wstage_wait(); __syncthreads(); int nf; const float* src = wsched(nd, args, 0, &nf); wstage_issue(wbuf, src, nf, NTHR); q = 0; }
             continue;
         }
         __syncthreads();
 
         // ---------------------------------- reverse ----------------------------------
-        dw_compute<NC, TP>(bufA, bufZ, LD, H, nd.d_out, part + nd.offW[L + 1], scratch, args.nsplit_cap);
-        if constexpr (WS) { const float* wl = w_consume(); gemm_rows<NC, UT, TP, true>(bufZ, LD, wl, nd.d_out, H, j0, p, acc); }
+        dw_compute<NC, TP>(bufA, bufZ, LD, H, nd.d_out, part + nd.offW[L + 1], scratch, nsplit_cap, NTHR);
+        if constexpr (WS) { const float* wl = w_consume(); gemm_rows<NC, UT, TP, true, KU>(bufZ, LD, wl, nd.d_out, H, j0, p, acc); }
         else gemm_rows<NC, UT, TP>(bufZ, LD, args.paramsT + nd.offW[L + 1], nd.d_out, H, j0, p, acc);
         __syncthreads();
-        dw_flush<NC, TP>(H, nd.d_out, part + nd.offW[L + 1], scratch, args.nsplit_cap);
+        dw_flush<NC, TP>(H, nd.d_out, part + nd.offW[L + 1], scratch, nsplit_cap, NTHR);
 
         for (int l = L; l >= 1; l--) {
             // elementwise adjoint of the tanh layer: acc = Abar_l  →  Zbar_l into bufZ
@@ -421,13 +425,13 @@ fused_step_fp32(const NetDims nd, const FusedArgs args) {
                         bufA[k * LD + c * TP + p] = (c == 0) ? x[k] : ((c == 1 + k) ? 1.0f : 0.0f);
             }
             __syncthreads();
-            dw_compute<NC, TP>(bufA, bufZ, LD, l == 1 ? DIN : H, H, part + nd.offW[l], scratch, args.nsplit_cap);
+            dw_compute<NC, TP>(bufA, bufZ, LD, l == 1 ? DIN : H, H, part + nd.offW[l], scratch, nsplit_cap, NTHR);
             if (l > 1) {
-                if constexpr (WS) { const float* wl = w_consume(); gemm_rows<NC, UT, TP, true>(bufZ, LD, wl, H, H, j0, p, acc); }
+                if constexpr (WS) { const float* wl = w_consume(); gemm_rows<NC, UT, TP, true, KU>(bufZ, LD, wl, H, H, j0, p, acc); }
                 else gemm_rows<NC, UT, TP>(bufZ, LD, args.paramsT + nd.offW[l], H, H, j0, p, acc);
             }
             __syncthreads();
-            dw_flush<NC, TP>(l == 1 ? DIN : H, H, part + nd.offW[l], scratch, args.nsplit_cap);
+            dw_flush<NC, TP>(l == 1 ? DIN : H, H, part + nd.offW[l], scratch, nsplit_cap, NTHR);
         }
         q = 0;                                          // the last prefetch of the tile was W_1 of the next one
     }
