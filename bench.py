@@ -33,7 +33,26 @@ CONFIG_NAMES = {
     4: "C4 2-D Allen-Cahn 3->[128x6]->1, 16,777,216 pts",
     5: "C5 2-D Navier-Stokes 3->[256x8]->3, 67,108,864 pts",
 }
-FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # CUDA-core FMA peak at max SM clock (derived)
+FP32_PEAK_DERIVED = 148 * 128 * 2 * 1.965e9 / 1e12    # CUDA-core FMA peak at max SM clock (derived)
+
+
+def fp32_peak():
+    """Measured FP32 FFMA peak of this pool's B200 (tests/cuda/fma_peak.cu → profiles/fp32_peak.json);
+    MEASURED_PEAKS.json has no FP32 entry, so this repo measured it itself.  Falls back to the derived figure."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "fp32_peak.json")) as f:
+            return float(json.load(f)["fp32_ffma_tflops"]), "measured (tests/cuda/fma_peak.cu, profiles/fp32_peak.json): register-only FFMA, 64 warps/SM"
+    except Exception:
+        return FP32_PEAK_DERIVED, "derived 148 SM x 128 FMA x 2 x 1.965 GHz"
+
+
+def traffic_for(which, prec_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel per launch from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(f"c{which}_{prec_name}")
+    except Exception:
+        return None
 
 
 def peaks():
@@ -176,7 +195,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("PINN_BENCH_PRECISION", "auto"),
                     choices=["auto", "fp32", "bf16x3", "bf16"],
                     help="contraction arithmetic: fp32 CUDA cores | bf16x3 / bf16 tcgen05 (width 64/128/256); "
-                         "auto = fp32 for width < 64, bf16x3 for 64/128, bf16 for 256")
+                         "auto = fp32 for width <= 64, bf16x3 for 128, bf16 for 256")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -211,7 +230,8 @@ def main():
     width = {1: 20, 2: 20, 3: 64, 4: 128, 5: 256}[which]
     prec_name = args.precision
     if prec_name == "auto":
-        prec_name = "fp32" if width < 64 else ("bf16x3" if width <= 128 else "bf16")
+        # measured on B200: at width 64 the FP32 CUDA-core kernel is as fast as the tcgen05 path, so keep FP32 there
+        prec_name = "fp32" if width <= 64 else ("bf16x3" if width <= 128 else "bf16")
     prec = {"fp32": P.PREC_FP32, "bf16x3": P.PREC_BF16X3, "bf16": P.PREC_BF16}[prec_name]
     cfg = P.default_config(which, n_interior=nf, n_boundary=nb, n_initial=n0, rank=rank, nranks=world,
                            device=local_rank, precision=prec)
@@ -298,12 +318,12 @@ def main():
             rf_src = f"{pk['source']} bf16_tflops_sustained (MEASURED_PEAKS.json); algorithmic FLOPs 6CW/pt, issued tensor FLOPs x{mma_mult}"
             rf_kernel = "fused_step_tc (interior, tcgen05 " + prec_name + ")"
         else:
-            rf_bound, rf_peak = "fp32_fma", FP32_PEAK_TFLOPS
-            rf_src = "derived 148 SM x 128 FMA x 2 x 1.965 GHz (CUDA-core path; no measured FP32 peak in MEASURED_PEAKS.json)"
+            rf_bound = "fp32_fma"
+            rf_peak, rf_src = fp32_peak()
             rf_kernel = "fused_step_fp32 (interior)"
         roofline = {
             "bound": rf_bound, "kernel": rf_kernel, "achieved": ach_tf, "peak": rf_peak,
-            "unit": "TFLOP/s", "frac": ach_tf / rf_peak, "traffic": None,
+            "unit": "TFLOP/s", "frac": ach_tf / rf_peak, "traffic": traffic_for(which, prec_name),
             "peak_source": rf_src, "issued_tensor_tflops": ach_tf * mma_mult if tensor_path else 0.0,
             "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step if ms_step else None,
             "hbm": {"achieved": ach_gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_gb / pk["hbm_gbs"], "of": pk["source"]},

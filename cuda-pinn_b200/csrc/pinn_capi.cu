@@ -14,6 +14,7 @@
 #include "pinn_device.cuh"
 #include "pinn_fused_fp32.cuh"
 #include "pinn_fused_tc.cuh"
+#include "pinn_fused_warp.cuh"
 
 using namespace pinn;
 
@@ -191,7 +192,8 @@ struct pinn_ctx {
     float scale[3] = {0, 0, 0};
     float* h_pinned = nullptr;          // [8]: loss record + flag
     // launch configuration of the fused kernels
-    fused_fn kern_full = nullptr, kern_val = nullptr;
+    fused_fn kern_full = nullptr, kern_val = nullptr, kern_warp = nullptr;   // kern_warp: warp-autonomous narrow-net kernel
+    int warp_wpc = 6, warp_smem = 0;
     int TP = 32, UT = 4, threads = 0, smem_full = 0, smem_val = 0, grid_cap_full = 0, grid_cap_val = 0;
     int rows_cap_a = 0, rows_cap_b = 0, nsplit_cap = 1, kernel_id = 0, num_sms = 148;
     long long stash_per_cta = 0;
@@ -200,7 +202,7 @@ struct pinn_ctx {
     tc_fn kern_tc = nullptr;
     __nv_bfloat16* d_wq = nullptr;
     long long wq_term_stride = 0;
-    int nterms = 0, tc_threads = 0, tc_smem = 0, tc_tmem_cols = 0, grid_cap_tc = 0;
+    int tc_ut = 8, nterms = 0, tc_threads = 0, tc_smem = 0, tc_tmem_cols = 0, grid_cap_tc = 0;
     AdamArgs adam{};
     void* comm = nullptr;
     std::string err;
@@ -375,17 +377,39 @@ static int configure_kernels(pinn_ctx* c) {
     c->grid_cap_full = occ_f * c->num_sms;
     c->grid_cap_val = occ_v * c->num_sms;
     c->kernel_id = (c->UT == 8 ? 10 : 0) + (c->TP == 16 ? 1 : 0);
+    // warp-autonomous kernel for the headline narrow network (Burgers 2 -> [20 x L] -> 1), training launches only
+    // Opt-in (PINN_WARP_KERNEL=1): measured on B200 it matches the block-tile kernel on C2 (125 vs 131 us) but its
+    // 217 KB of shared memory keeps the concurrent boundary/initial launch off the SMs (step 193 vs 146 us).
+    if (c->cfg.precision == PINN_PREC_FP32 && H == 20 && nd.d_in == 2 && nd.n2 == 1 && getenv("PINN_WARP_KERNEL")) {
+        c->kern_warp = fused_step_warp<2, 1, 20, 6>;
+        c->warp_wpc = 6;
+        const int P4 = (nd.P + 3) & ~3;
+        c->warp_smem = (2 * P4 + c->warp_wpc * (3 * H + 1) * (nd.C * 32 + 4)) * (int)sizeof(float);
+        if (c->warp_smem <= max_smem) {
+            CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, c->warp_smem));
+            c->kernel_id = 50;
+        } else {
+            c->kern_warp = nullptr;
+        }
+    }
     if (c->cfg.precision != PINN_PREC_FP32) {
         // tensor-core kernel for the interior set; boundary / initial points keep the FP32 kernel
         const int nterms = c->cfg.precision == PINN_PREC_BF16X3 ? 2 : 1;
         if (!(H == 64 || H == 128 || H == 256))
             return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: the tensor-core path is built for width 64, 128 or 256 (use PINN_PREC_FP32)");
-        if (nd.d_in == 2 && nd.n2 == 1) c->kern_tc = nterms == 2 ? fused_step_tc<2, 1, 2> : fused_step_tc<2, 1, 1>;
-        else if (nd.d_in == 2 && nd.n2 == 2) c->kern_tc = nterms == 2 ? fused_step_tc<2, 2, 2> : fused_step_tc<2, 2, 1>;
-        else c->kern_tc = nterms == 2 ? fused_step_tc<3, 2, 2> : fused_step_tc<3, 2, 1>;
+        // PINN_TC_UT=4|8 overrides the unit group (threads = 16 * H / UT); default: measured best per width
+        int ut = 8;
+        if (const char* e = getenv("PINN_TC_UT")) ut = atoi(e) == 4 ? 4 : 8;
+        c->tc_ut = ut;
+#define PICK_TC(D, N) (nterms == 2 ? (ut == 4 ? fused_step_tc<D, N, 2, 4> : fused_step_tc<D, N, 2, 8>) \
+                                   : (ut == 4 ? fused_step_tc<D, N, 1, 4> : fused_step_tc<D, N, 1, 8>))
+        if (nd.d_in == 2 && nd.n2 == 1) c->kern_tc = PICK_TC(2, 1);
+        else if (nd.d_in == 2 && nd.n2 == 2) c->kern_tc = PICK_TC(2, 2);
+        else c->kern_tc = PICK_TC(3, 2);
+#undef PICK_TC
         const int HW = H > 128 ? 128 : H;
         c->nterms = nterms;
-        c->tc_threads = 2 * H;
+        c->tc_threads = 16 * H / c->tc_ut;
         c->tc_smem = nterms * (2 * H * 256 + HW * H * 2);
         if (c->tc_smem > max_smem)
             return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: PINN_PREC_BF16X3 needs width <= 128 (operand terms do not fit in shared memory)");
@@ -433,8 +457,12 @@ static int launch_fused(pinn_ctx* c, cudaStream_t stream, bool full, const Point
         total = 0;
         for (int i = 0; i < nsets; i++) { a.sets[i].ntiles = tiles_of(a.sets[i].n, 16); total += a.sets[i].ntiles; }
     }
+    const bool wk = full && mode == 0 && !tc && c->kern_warp != nullptr;
     const int cap = tc ? c->grid_cap_tc : (full ? c->grid_cap_full : c->grid_cap_val);
-    const int grid = total < cap ? total : cap;
+    int grid = total < cap ? total : cap;
+    if (wk) {                                             // one warp per 32-point tile, WPC warps per CTA, one CTA per SM
+        grid = total < c->num_sms ? total : c->num_sms;        // spread tiles over the SMs first, then over warps
+    }
     const bool timed = c->prof && full && mode == 0 && !c->capturing;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {
@@ -445,12 +473,14 @@ static int launch_fused(pinn_ctx* c, cudaStream_t stream, bool full, const Point
         TcArgs ta{};
         ta.f = a; ta.wq = c->d_wq; ta.wq_term_stride = c->wq_term_stride; ta.tmem_cols = c->tc_tmem_cols;
         c->kern_tc<<<grid, c->tc_threads, c->tc_smem, stream>>>(c->nd, ta);
+    } else if (wk) {
+        c->kern_warp<<<grid, c->warp_wpc * 32, c->warp_smem, stream>>>(c->nd, a);
     } else {
         (full ? c->kern_full : c->kern_val)<<<grid, c->threads, full ? c->smem_full : c->smem_val, stream>>>(c->nd, a);
     }
     if (timed) { cudaEventRecord(e1, stream); c->pending.emplace_back(e0, e1); }
     if (full) c->last_grid = grid;
-    if (grid_out) *grid_out = grid;
+    if (grid_out) *grid_out = wk ? grid * c->warp_wpc : grid;      // partial / stash rows this launch used
     c->step_launches++;
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
     return PINN_OK;
@@ -642,12 +672,15 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     // evaluation calls), [rows_cap_a, rows_cap_a + rows_cap_b) the concurrent boundary/initial launch
     c->rows_cap_a = c->grid_cap_full > c->grid_cap_tc ? c->grid_cap_full : c->grid_cap_tc;
     if (c->grid_cap_val > c->rows_cap_a) c->rows_cap_a = c->grid_cap_val;      // pinn_forward uses the value kernel on rows A
+    if (c->kern_warp && c->num_sms * c->warp_wpc > c->rows_cap_a) c->rows_cap_a = c->num_sms * c->warp_wpc;
     c->rows_cap_b = c->grid_cap_val;
     const size_t nrows = (size_t)c->rows_cap_a + c->rows_cap_b;
     c->stash_per_cta = (long long)nd.L * nd.C * nd.H * c->TP;   // the tensor-core kernel (16-point tiles) needs no more
     const size_t P = nd.P;
-    TRY_C(cudaMalloc(&c->d_params, P * sizeof(float)));
-    TRY_C(cudaMalloc(&c->d_paramsT, P * sizeof(float)));
+    TRY_C(cudaMalloc(&c->d_params, (P + 4) * sizeof(float)));     // +4: kernels copy them in float4 units
+    TRY_C(cudaMalloc(&c->d_paramsT, (P + 4) * sizeof(float)));
+    TRY_C(cudaMemsetAsync(c->d_params, 0, (P + 4) * sizeof(float), c->stream));
+    TRY_C(cudaMemsetAsync(c->d_paramsT, 0, (P + 4) * sizeof(float), c->stream));
     TRY_C(cudaMalloc(&c->d_m, P * sizeof(float)));
     TRY_C(cudaMalloc(&c->d_v, P * sizeof(float)));
     TRY_C(cudaMalloc(&c->d_gbuf, (size_t)nd.PP * sizeof(float)));
@@ -921,7 +954,8 @@ int pinn_profile_get(pinn_ctx* c, pinn_profile* out, int reset) {
     cudaSetDevice(c->cfg.device);
     drain_profile(c);
     out->launches = c->launches; out->step_kernel_ms = c->kernel_ms; out->step_kernel_count = c->kernel_count;
-    out->grid = c->last_grid; out->block = c->kern_tc ? c->tc_threads : c->threads; out->smem_bytes = c->kern_tc ? c->tc_smem : c->smem_full; out->kernel_id = c->kernel_id;
+    out->grid = c->last_grid; out->block = c->kern_tc ? c->tc_threads : (c->kern_warp ? c->warp_wpc * 32 : c->threads);
+    out->smem_bytes = c->kern_tc ? c->tc_smem : (c->kern_warp ? c->warp_smem : c->smem_full); out->kernel_id = c->kernel_id;
     if (reset) { c->launches = 0; c->kernel_ms = 0.0; c->kernel_count = 0; }
     return PINN_OK;
 }

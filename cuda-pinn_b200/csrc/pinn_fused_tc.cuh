@@ -37,10 +37,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
-template <int DIN, int N2, int NTERMS>
-__global__ void __launch_bounds__(512)
+// UT = units per thread (8: one 16-byte operand chunk per channel, 2H threads; 4: half a chunk,
+// 4H threads at <= 64 registers — twice the resident warps to hide the serialized phase latencies).
+template <int DIN, int N2, int NTERMS, int UT>
+__global__ void __launch_bounds__(UT == 8 ? 512 : 1024, 1)
 fused_step_tc(const NetDims nd, const TcArgs ta) {
-    constexpr int NC = 1 + DIN + N2, TP = 16, UT = 8, R = 128;
+    constexpr int NC = 1 + DIN + N2, TP = 16, R = 128;
+    static_assert(UT == 8 || UT == 4, "unit group of 4 or 8");
     constexpr int LD = NC * TP + 2;                   // staging leading dimension (floats)
     constexpr int RV = NC * TP;                       // valid rows of the 128-row tile
     const FusedArgs& args = ta.f;
@@ -56,7 +59,7 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
     uint8_t* bufZ = bufA + NTERMS * opBytes;
     uint8_t* bufW = bufZ + NTERMS * opBytes;
     float* Zs = reinterpret_cast<float*>(smem_raw);   // FP32 staging [unit][LD], aliases bufA|bufZ
-    float* xbuf = reinterpret_cast<float*>(bufZ);     // output-layer exchange, aliases bufZ
+    float* xbuf = reinterpret_cast<float*>(smem_raw); // output-layer exchange [H/UT][3][NC][16] + seeds, aliases the dead operands
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int p = tid % TP, g = tid / TP, j0 = g * UT;
@@ -94,28 +97,36 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
     };
     // ---- operand write: thread (p, g) stores its 8 units of every channel as one 16-byte chunk ----
     auto write_operand = [&](uint8_t* buf, const float (&v)[NC][UT], bool zero_pad) {
+        // chunk of 8 features = 16 bytes; this thread owns UT of them starting at feature j0
+        const size_t coff = (size_t)(j0 >> 3) * (R * 16) + (size_t)(j0 & 7) * 2;
         #pragma unroll
         for (int c = 0; c < NC; c++) {
-            uint4 hi;
-            hi.x = pack_bf16x2(v[c][0], v[c][1]); hi.y = pack_bf16x2(v[c][2], v[c][3]);
-            hi.z = pack_bf16x2(v[c][4], v[c][5]); hi.w = pack_bf16x2(v[c][6], v[c][7]);
-            uint8_t* dst = buf + (size_t)g * (R * 16) + (size_t)(c * TP + p) * 16;
-            *reinterpret_cast<uint4*>(dst) = hi;
+            uint8_t* dst = buf + coff + (size_t)(c * TP + p) * 16;
+            uint32_t hi[UT / 2];
+            #pragma unroll
+            for (int h = 0; h < UT / 2; h++) hi[h] = pack_bf16x2(v[c][2 * h], v[c][2 * h + 1]);
+            if constexpr (UT == 8) *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            else *reinterpret_cast<uint2*>(dst) = make_uint2(hi[0], hi[1]);
             if constexpr (NTERMS == 2) {
-                float r[UT];
+                uint32_t mid[UT / 2];
                 #pragma unroll
-                for (int u = 0; u < UT; u++) r[u] = v[c][u] - __bfloat162float(__float2bfloat16(v[c][u]));
-                uint4 mid;
-                mid.x = pack_bf16x2(r[0], r[1]); mid.y = pack_bf16x2(r[2], r[3]);
-                mid.z = pack_bf16x2(r[4], r[5]); mid.w = pack_bf16x2(r[6], r[7]);
-                *reinterpret_cast<uint4*>(dst + opBytes) = mid;
+                for (int h = 0; h < UT / 2; h++) {
+                    const float r0 = v[c][2 * h] - __bfloat162float(__float2bfloat16(v[c][2 * h]));
+                    const float r1 = v[c][2 * h + 1] - __bfloat162float(__float2bfloat16(v[c][2 * h + 1]));
+                    mid[h] = pack_bf16x2(r0, r1);
+                }
+                if constexpr (UT == 8) *reinterpret_cast<uint4*>(dst + opBytes) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+                else *reinterpret_cast<uint2*>(dst + opBytes) = make_uint2(mid[0], mid[1]);
             }
         }
         if (zero_pad) {                               // rows >= NC*16 are the K-padding of the dW contraction
             for (int rr = RV + p; rr < R; rr += TP)
                 #pragma unroll
-                for (int t = 0; t < NTERMS; t++)
-                    *reinterpret_cast<uint4*>(buf + t * opBytes + (size_t)g * (R * 16) + (size_t)rr * 16) = make_uint4(0, 0, 0, 0);
+                for (int t = 0; t < NTERMS; t++) {
+                    uint8_t* dst = buf + t * opBytes + coff + (size_t)rr * 16;
+                    if constexpr (UT == 8) *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+                    else *reinterpret_cast<uint2*>(dst) = make_uint2(0, 0);
+                }
         }
     };
     // ---- accumulator rows TMEM -> FP32 staging -> thread (p, g) registers ----
@@ -326,7 +337,7 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                     acc[c][u] = s;
                 }
         }
-        __syncthreads();                                  // ybuf (aliases bufZ) is free
+        __syncthreads();                                  // xbuf / ybuf (alias bufA | bufZ) are free
 
         // ---------------- reverse pass ----------------
         for (int l = L; l >= 1; l--) {
