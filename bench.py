@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("PINN_BENCH_PRECISION", "auto"),
                     choices=["auto", "fp32", "bf16x3", "bf16"],
                     help="contraction arithmetic: fp32 CUDA cores | bf16x3 / bf16 tcgen05 (width 64/128/256); "
-                         "auto = fp32 for width <= 64, bf16x3 for 128, bf16 for 256")
+                         "auto = fp32 for width < 64, bf16x3 for 64/128, bf16 for 256")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -230,8 +230,7 @@ def main():
     width = {1: 20, 2: 20, 3: 64, 4: 128, 5: 256}[which]
     prec_name = args.precision
     if prec_name == "auto":
-        # measured on B200: at width 64 the FP32 CUDA-core kernel is as fast as the tcgen05 path, so keep FP32 there
-        prec_name = "fp32" if width <= 64 else ("bf16x3" if width <= 128 else "bf16")
+        prec_name = "fp32" if width < 64 else ("bf16x3" if width <= 128 else "bf16")
     prec = {"fp32": P.PREC_FP32, "bf16x3": P.PREC_BF16X3, "bf16": P.PREC_BF16}[prec_name]
     cfg = P.default_config(which, n_interior=nf, n_boundary=nb, n_initial=n0, rank=rank, nranks=world,
                            device=local_rank, precision=prec)

@@ -195,6 +195,7 @@ struct pinn_ctx {
     fused_fn kern_full = nullptr, kern_val = nullptr, kern_warp = nullptr;   // kern_warp: warp-autonomous narrow-net kernel
     int warp_wpc = 6, warp_smem = 0;
     int TP = 32, UT = 4, threads = 0, smem_full = 0, smem_val = 0, grid_cap_full = 0, grid_cap_val = 0;
+    int val_TP = 32, val_UT = 4, val_threads = 0;   // value-only (boundary / initial / pinn_forward) launch shape
     int rows_cap_a = 0, rows_cap_b = 0, nsplit_cap = 1, kernel_id = 0, num_sms = 148;
     long long stash_per_cta = 0;
     // tensor-core path (precision != FP32): interior set only
@@ -320,6 +321,9 @@ static fused_fn pick_ut_tp(int UT, int TP) {
     if (UT == 4 && TP == 32) return fused_step_fp32<DIN, N2, FULL, 4, 32, 256, 4>;
     if (UT == 8 && TP == 32) return fused_step_fp32<DIN, N2, FULL, 8, 32, 512, 1>;
     if (UT == 8 && TP == 16) return fused_step_fp32<DIN, N2, FULL, 8, 16, 512, 1>;
+    if constexpr (!FULL) {      // value-only kernel of wide nets: 32 units per thread (32 FFMAs per 1 LDS + 8 LDG.128)
+        if (UT == 32 && TP == 32) return fused_step_fp32<DIN, N2, FULL, 32, 32, 256, 1>;
+    }
     return nullptr;
 }
 static fused_fn pick_kernel(int d_in, int n2, bool full, int UT, int TP, int H) {
@@ -363,15 +367,21 @@ static int configure_kernels(pinn_ctx* c) {
     const int scratch = c->nsplit_cap > 1 ? c->threads * 16 * (int)sizeof(float) : 0;
     const int wstage = c->UT == 4 ? 2 * rows * rows * (int)sizeof(float) : 0;     // cp.async weight double buffer
     c->smem_full = smem_for(nd.C, c->TP) + scratch + wstage;
-    c->smem_val = smem_for(1, c->TP) + scratch + wstage;
+    c->val_UT = c->UT; c->val_TP = c->TP; c->val_threads = c->threads;
+    int scratch_val = scratch;
+    if (H >= 64 && H % 32 == 0) {                         // wide nets: one channel only, so take 32 units per thread
+        c->val_UT = 32; c->val_TP = 32; c->val_threads = 32 * (H / 32);
+        scratch_val = c->nsplit_cap > 1 ? c->val_threads * 16 * (int)sizeof(float) : 0;
+    }
+    c->smem_val = smem_for(1, c->val_TP) + scratch_val + wstage;
     c->kern_full = pick_kernel(nd.d_in, nd.n2, true, c->UT, c->TP, H);
-    c->kern_val = pick_kernel(nd.d_in, nd.n2, false, c->UT, c->TP, H);
+    c->kern_val = pick_kernel(nd.d_in, nd.n2, false, c->val_UT, c->val_TP, H);
     if (!c->kern_full || !c->kern_val) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: no kernel for this configuration");
     CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_full, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_full));
     CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_val, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_val));
     int occ_f = 0, occ_v = 0;
     CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, c->kern_full, c->threads, c->smem_full));
-    CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_v, c->kern_val, c->threads, c->smem_val));
+    CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_v, c->kern_val, c->val_threads, c->smem_val));
     if (occ_f < 1 || occ_v < 1) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: fused kernel does not fit on an SM");
     if (occ_v > 4) occ_v = 4;
     c->grid_cap_full = occ_f * c->num_sms;
@@ -397,16 +407,17 @@ static int configure_kernels(pinn_ctx* c) {
         const int nterms = c->cfg.precision == PINN_PREC_BF16X3 ? 2 : 1;
         if (!(H == 64 || H == 128 || H == 256))
             return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: the tensor-core path is built for width 64, 128 or 256 (use PINN_PREC_FP32)");
-        // PINN_TC_UT=4|8 overrides the unit group (threads = 16 * H / UT); default: measured best per width
-        int ut = 8;
-        if (const char* e = getenv("PINN_TC_UT")) ut = atoi(e) == 4 ? 4 : 8;
+        const int ut = 8;
         c->tc_ut = ut;
-#define PICK_TC(D, N) (nterms == 2 ? (ut == 4 ? fused_step_tc<D, N, 2, 4> : fused_step_tc<D, N, 2, 8>) \
-                                   : (ut == 4 ? fused_step_tc<D, N, 1, 4> : fused_step_tc<D, N, 1, 8>))
+#define PICK_TC_H(D, N, HH) (nterms == 2 ? fused_step_tc<D, N, 2, 8, HH> : fused_step_tc<D, N, 1, 8, HH>)
+#define PICK_TC(D, N) (H == 64 ? PICK_TC_H(D, N, 64) : (H == 128 ? PICK_TC_H(D, N, 128) : fused_step_tc<D, N, 1, 8, 256>))
+        if (nterms == 2 && H == 256)
+            return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: PINN_PREC_BF16X3 needs width <= 128 (operand terms do not fit in shared memory)");
         if (nd.d_in == 2 && nd.n2 == 1) c->kern_tc = PICK_TC(2, 1);
         else if (nd.d_in == 2 && nd.n2 == 2) c->kern_tc = PICK_TC(2, 2);
         else c->kern_tc = PICK_TC(3, 2);
 #undef PICK_TC
+#undef PICK_TC_H
         const int HW = H > 128 ? 128 : H;
         c->nterms = nterms;
         c->tc_threads = 16 * H / c->tc_ut;
@@ -476,7 +487,8 @@ static int launch_fused(pinn_ctx* c, cudaStream_t stream, bool full, const Point
     } else if (wk) {
         c->kern_warp<<<grid, c->warp_wpc * 32, c->warp_smem, stream>>>(c->nd, a);
     } else {
-        (full ? c->kern_full : c->kern_val)<<<grid, c->threads, full ? c->smem_full : c->smem_val, stream>>>(c->nd, a);
+        if (full) c->kern_full<<<grid, c->threads, c->smem_full, stream>>>(c->nd, a);
+        else c->kern_val<<<grid, c->val_threads, c->smem_val, stream>>>(c->nd, a);
     }
     if (timed) { cudaEventRecord(e1, stream); c->pending.emplace_back(e0, e1); }
     if (full) c->last_grid = grid;
@@ -493,7 +505,7 @@ static int run_local(pinn_ctx* c, int bump_step) {
     for (int k = 1; k <= 2; k++) {
         if (c->n_local[k] == 0) continue;
         v[nv].x = c->d_x[k]; v[nv].n = c->n_local[k]; v[nv].scale = c->scale[k]; v[nv].set = k;
-        v[nv].ntiles = tiles_of(c->n_local[k], c->TP); nv++;
+        v[nv].ntiles = tiles_of(c->n_local[k], c->val_TP); nv++;
     }
     if (nv) {
         CUDA_TRY(c, "pinn_train_step", cudaEventRecord(c->ev_fork, c->stream));
@@ -676,6 +688,7 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     c->rows_cap_b = c->grid_cap_val;
     const size_t nrows = (size_t)c->rows_cap_a + c->rows_cap_b;
     c->stash_per_cta = (long long)nd.L * nd.C * nd.H * c->TP;   // the tensor-core kernel (16-point tiles) needs no more
+    if ((long long)nd.L * nd.H * c->val_TP > c->stash_per_cta) c->stash_per_cta = (long long)nd.L * nd.H * c->val_TP;
     const size_t P = nd.P;
     TRY_C(cudaMalloc(&c->d_params, (P + 4) * sizeof(float)));     // +4: kernels copy them in float4 units
     TRY_C(cudaMalloc(&c->d_paramsT, (P + 4) * sizeof(float)));
@@ -892,7 +905,7 @@ static int eval_common(pinn_ctx* c, const char* fn, bool full, const float* x, f
     if (full) CUDA_TRY(c, fn, cudaMallocAsync(&dr, n * nd.n_res * sizeof(float), c->stream));
     CUDA_TRY(c, fn, cudaMemcpyAsync(dx, x, n * nd.d_in * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     PointSet s{};
-    s.x = dx; s.n = n; s.scale = 0.0f; s.set = full ? PINN_SET_INTERIOR : PINN_SET_BOUNDARY; s.ntiles = tiles_of(n, c->TP);
+    s.x = dx; s.n = n; s.scale = 0.0f; s.set = full ? PINN_SET_INTERIOR : PINN_SET_BOUNDARY; s.ntiles = tiles_of(n, full ? c->TP : c->val_TP);
     c->step_launches = 0;
     int rc = launch_fused(c, c->stream, full, &s, 1, 1, dy, dr, 0, nullptr);
     c->launches += c->step_launches;

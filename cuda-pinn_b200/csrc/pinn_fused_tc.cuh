@@ -39,8 +39,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 // UT = units per thread (8: one 16-byte operand chunk per channel, 2H threads; 4: half a chunk,
 // 4H threads at <= 64 registers — twice the resident warps to hide the serialized phase latencies).
-template <int DIN, int N2, int NTERMS, int UT>
-__global__ void __launch_bounds__(UT == 8 ? 512 : 1024, 1)
+// HT: hidden width fixed at compile time (64 / 128 / 256): offsets fold to immediates.
+template <int DIN, int N2, int NTERMS, int UT, int HT>
+__global__ void __launch_bounds__(16 * HT / UT, 512 / (16 * HT / UT))
 fused_step_tc(const NetDims nd, const TcArgs ta) {
     constexpr int NC = 1 + DIN + N2, TP = 16, R = 128;
     static_assert(UT == 8 || UT == 4, "unit group of 4 or 8");
@@ -51,10 +52,11 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
     __shared__ uint64_t mma_bar, w_bar;
     __shared__ uint32_t tmem_slot;
 
-    const int H = nd.H, L = nd.L;
-    const int HW = H > 128 ? 128 : H, nhalf = H / HW, mt = (H + 127) >> 7;
-    const uint32_t opBytes = (uint32_t)H * 256u;      // one operand term: [H/8][128][16 B]
-    const uint32_t wBytes = (uint32_t)HW * H * 2u;    // one weight term (one half for H = 256)
+    constexpr int H = HT;
+    const int L = nd.L;
+    constexpr int HW = H > 128 ? 128 : H, nhalf = H / HW, mt = (H + 127) >> 7;
+    constexpr uint32_t opBytes = (uint32_t)H * 256u;  // one operand term: [H/8][128][16 B]
+    constexpr uint32_t wBytes = (uint32_t)HW * H * 2u; // one weight term (one half for H = 256)
     uint8_t* bufA = smem_raw;
     uint8_t* bufZ = bufA + NTERMS * opBytes;
     uint8_t* bufW = bufZ + NTERMS * opBytes;
@@ -63,10 +65,11 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int p = tid % TP, g = tid / TP, j0 = g * UT;
-    const int nwarps = blockDim.x >> 5, lg = warp & 3, wsub = warp >> 2, nsub = nwarps >> 2;
+    constexpr int nwarps = (16 * H / UT) >> 5, nsub = nwarps >> 2;
+    const int lg = warp & 3, wsub = warp >> 2;
     float* stash = args.stash + (size_t)(args.row0 + blockIdx.x) * args.stash_per_cta;
     float* part = args.partial + (size_t)(args.row0 + blockIdx.x) * nd.PP;
-    const size_t lstride = (size_t)NC * H * TP;
+    constexpr int lstride = NC * H * TP;
 
     if (warp == 0) umma::tmem_alloc(&tmem_slot, (uint32_t)ta.tmem_cols);
     if (tid == 0) { umma::mbar_init(&mma_bar, 1); umma::mbar_init(&w_bar, 1); umma::mbar_fence_init(); }
@@ -250,7 +253,7 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
 
         // ---------------- output layer + residual + seeds: CUDA cores ----------------
         // acc = A_L (FP32).  Partial outputs over this thread's 8 units, summed over groups through smem.
-        const int G = H / UT;
+        constexpr int G = H / UT;
         const float* Wo = args.params + nd.offW[L + 1];
         float wo[UT][3];
         #pragma unroll
