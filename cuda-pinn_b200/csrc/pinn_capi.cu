@@ -569,17 +569,25 @@ static void drop_graph(pinn_ctx* c) {
     c->graph_exec = nullptr; c->graph = nullptr;
 }
 
-// One training step: replay of a captured CUDA graph (interior || boundary/initial -> reduce ->
-// all-reduce -> Adam) unless per-kernel profiling is on.  Re-captured when the point counts change.
+// One training step.  The device work that is local to this GPU is replayed from a captured CUDA graph
+// (single GPU: interior || boundary/initial -> reduce -> Adam; with a communicator: interior ||
+// boundary/initial -> reduce only).  NCCL is never captured: its lazy first-call setup is not
+// capturable and a failed capture would leave the ranks out of step, so the all-reduce and the Adam
+// kernel that follows it are launched directly.  Per-kernel profiling disables the graph.
 static int step_once(pinn_ctx* c) {
     const bool want_graph = c->graph_ok && !c->prof;
+    const bool dist = c->cfg.nranks > 1 && c->comm != nullptr;
     if (want_graph) {
-        const uint64_t key[4] = {c->n_local[0], c->n_local[1], c->n_local[2], (uint64_t)(c->comm != nullptr)};
+        const uint64_t key[4] = {c->n_local[0], c->n_local[1], c->n_local[2], (uint64_t)dist};
         if (!c->graph_exec || memcmp(key, c->graph_key, sizeof(key)) != 0) {
             drop_graph(c);
             c->step_launches = 0; c->capturing = true;
             cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
-            int rc = (e == cudaSuccess) ? issue_step(c) : PINN_ERR_CUDA;
+            int rc = PINN_ERR_CUDA;
+            if (e == cudaSuccess) {
+                rc = run_local(c, 1);
+                if (!rc && !dist) rc = run_apply(c, 1);
+            }
             cudaGraph_t g = nullptr;
             if (e == cudaSuccess) e = cudaStreamEndCapture(c->stream, &g);
             c->capturing = false;
@@ -596,6 +604,13 @@ static int step_once(pinn_ctx* c) {
         if (c->graph_exec) {
             CUDA_TRY(c, "pinn_train_step", cudaGraphLaunch(c->graph_exec, c->stream));
             c->launches += c->launches_per_graph;
+            if (dist) {
+                c->step_launches = 0;
+                int rc = run_allreduce(c);
+                if (!rc) rc = run_apply(c, 1);
+                c->launches += c->step_launches;
+                if (rc) return rc;
+            }
             c->host_step++;
             return PINN_OK;
         }
