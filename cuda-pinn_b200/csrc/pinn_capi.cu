@@ -203,7 +203,8 @@ struct pinn_ctx {
     tc_fn kern_tc = nullptr;
     __nv_bfloat16* d_wq = nullptr;
     long long wq_term_stride = 0;
-    int tc_shared_rows = 0;          // > 0: tensor-core CTAs share this many L2-resident partial rows
+    int tc_shared_rows = 0;          // > 0: tensor-core CTAs share this many L2-resident partial rows (experiment knob)
+    uint8_t* d_ring = nullptr; long long ring_per_cta = 0; int tc_defer_g = 0;   // deferred dW (width 256)
     int tc_ut = 8, nterms = 0, tc_threads = 0, tc_smem = 0, tc_tmem_cols = 0, grid_cap_tc = 0;
     AdamArgs adam{};
     void* comm = nullptr;
@@ -435,6 +436,12 @@ static int configure_kernels(pinn_ctx* c) {
         c->grid_cap_tc = occ * c->num_sms;
         c->kernel_id = 100 + nterms;
         if (const char* e = getenv("PINN_TC_SHARED_ROWS")) c->tc_shared_rows = atoi(e);
+        if (H == 256 && nterms == 1 && nd.L >= 2) {
+            c->tc_defer_g = 16;
+            if (const char* e = getenv("PINN_TC_DEFER")) c->tc_defer_g = atoi(e);
+            if (c->tc_defer_g < 0 || c->tc_defer_g > 64) c->tc_defer_g = 0;
+            c->ring_per_cta = (long long)c->tc_defer_g * (nd.L - 1) * 2 * (H / 8) * (nd.C * 16) * 16;
+        }
     }
     return PINN_OK;
 }
@@ -487,6 +494,7 @@ static int launch_fused(pinn_ctx* c, cudaStream_t stream, bool full, const Point
     if (tc) {
         TcArgs ta{};
         ta.f = a; ta.wq = c->d_wq; ta.wq_term_stride = c->wq_term_stride; ta.tmem_cols = c->tc_tmem_cols;
+        ta.op_ring = c->d_ring; ta.ring_per_cta = c->ring_per_cta; ta.defer_g = (mode == 0) ? c->tc_defer_g : 0;
         c->kern_tc<<<grid, c->tc_threads, c->tc_smem, stream>>>(c->nd, ta);
     } else if (wk) {
         c->kern_warp<<<grid, c->warp_wpc * 32, c->warp_smem, stream>>>(c->nd, a);
@@ -722,6 +730,7 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
         c->wq_term_stride = (long long)(nd.L - 1) * nd.H * nd.H;
         TRY_C(cudaMalloc(&c->d_wq, (size_t)c->nterms * c->wq_term_stride * sizeof(__nv_bfloat16)));
     }
+    if (c->tc_defer_g > 0) TRY_C(cudaMalloc(&c->d_ring, (size_t)c->grid_cap_tc * c->ring_per_cta));
     TRY_C(cudaMalloc(&c->d_loss, 4 * sizeof(float)));
     TRY_C(cudaMalloc(&c->d_step, sizeof(unsigned long long)));
     TRY_C(cudaMalloc(&c->d_flag, sizeof(int)));
@@ -754,7 +763,7 @@ void pinn_destroy(pinn_ctx* c) {
     for (int k = 0; k < 3; k++) cudaFree(c->d_x[k]);
     cudaFree(c->d_params); cudaFree(c->d_paramsT); cudaFree(c->d_m); cudaFree(c->d_v);
     cudaFree(c->d_gbuf); cudaFree(c->d_partial); cudaFree(c->d_stash); cudaFree(c->d_loss);
-    cudaFree(c->d_step); cudaFree(c->d_flag); cudaFree(c->d_wq);
+    cudaFree(c->d_step); cudaFree(c->d_flag); cudaFree(c->d_wq); cudaFree(c->d_ring);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     drop_graph(c);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);

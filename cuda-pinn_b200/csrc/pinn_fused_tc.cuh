@@ -30,6 +30,12 @@ struct TcArgs {
     const __nv_bfloat16* wq;     // [NTERMS][L-1][H*H] chunk-major BF16 mirror of W_2..W_L
     long long wq_term_stride;    // elements between the hi and mid mirrors
     int tmem_cols;               // TMEM columns to allocate (power of two)
+    // Deferred dW (width 256): the two BF16 dW operands of every tile-layer go to a per-CTA ring by
+    // TMA bulk store; every `defer_g` tiles a catch-up pass streams them back and accumulates dW_l in
+    // TMEM over all of them, so the 256 KB flush happens once per defer_g tiles instead of every tile.
+    uint8_t* op_ring;            // [grid][defer_g][L-1][2][ (H/8) * RV * 16 bytes ]
+    long long ring_per_cta;      // bytes
+    int defer_g;                 // 0 = flush dW every tile
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -49,7 +55,7 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
     constexpr int RV = NC * TP;                       // valid rows of the 128-row tile
     const FusedArgs& args = ta.f;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ uint64_t mma_bar, w_bar;
+    __shared__ uint64_t mma_bar, w_bar, ld_bar[2], done_bar[2];
     __shared__ uint32_t tmem_slot;
 
     constexpr int H = HT;
@@ -72,7 +78,11 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
     constexpr int lstride = NC * H * TP;
 
     if (warp == 0) umma::tmem_alloc(&tmem_slot, (uint32_t)ta.tmem_cols);
-    if (tid == 0) { umma::mbar_init(&mma_bar, 1); umma::mbar_init(&w_bar, 1); umma::mbar_fence_init(); }
+    if (tid == 0) {
+        umma::mbar_init(&mma_bar, 1); umma::mbar_init(&w_bar, 1);
+        umma::mbar_init(&ld_bar[0], 1); umma::mbar_init(&ld_bar[1], 1); umma::mbar_init(&done_bar[0], 1); umma::mbar_init(&done_bar[1], 1);
+        umma::mbar_fence_init();
+    }
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
@@ -167,6 +177,73 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
         }
     };
     auto wait_mma = [&]() { umma::mbar_wait(&mma_bar, mma_phase); mma_phase ^= 1; };
+
+    // ---- deferred dW (see TcArgs) ----
+    constexpr uint32_t OPV = (uint32_t)(H / 8) * RV * 16;          // one stored operand: valid rows only
+    const bool defer = (!da_separate) && ta.defer_g > 0 && NTERMS == 1;
+    uint8_t* ring = ta.op_ring + (size_t)blockIdx.x * ta.ring_per_cta;
+    int gcount = 0;                                                 // tiles stored since the last catch-up
+    uint32_t ld_ph = 0, done_ph = 0;                                // phase bits of ld_bar[s] / done_bar[s] (thread 0)
+    auto drain_dw_to = [&](float* dst) {                           // TMEM [fan-in k][unit j] -> partial row, single owner
+        umma::tc_fence_after();
+        for (int tt = 0; tt < mt; tt++) {
+            if (tt * 128 + lg * 32 < H) {
+                const int k = tt * 128 + lg * 32 + lane;
+                const int c0 = wsub * (H / nsub);
+                for (int c = c0; c < c0 + H / nsub; c += 16) {
+                    uint32_t r[16];
+                    umma::tmem_ld16_nowait(tmem + ((uint32_t)(lg * 32) << 16) + tt * H + c, r);
+                    umma::tmem_ld_wait();
+                    float4* d4 = reinterpret_cast<float4*>(dst + (size_t)k * H + c);
+                    if (k < H) {
+                        #pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            atomicAdd(d4 + q, make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
+                                                          __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
+                    }
+                }
+            }
+        }
+        umma::tc_fence_before();
+    };
+    auto catch_up = [&](int cnt) {
+        if (tid == 0) umma::bulk_wait_all();                        // every operand store of these tiles has landed
+        __syncthreads();
+        for (int l = 2; l <= L; l++) {
+            if (tid == 0) {
+                umma::tc_fence_after();
+                auto load_item = [&](int i) {
+                    const int s = i & 1;
+                    uint8_t* stg = smem_raw + (size_t)s * 2 * OPV;
+                    const uint8_t* src = ring + ((size_t)(i * (L - 1) + (l - 2)) * 2) * OPV;
+                    umma::mbar_expect_tx(&ld_bar[s], 2 * OPV);
+                    umma::bulk_g2s(stg, src, 2 * OPV, &ld_bar[s]);  // A operand then Zbar operand, contiguous in the ring
+                };
+                load_item(0);
+                for (int i = 0; i < cnt; i++) {
+                    const int s = i & 1;
+                    if (i + 1 < cnt) {
+                        if (i >= 1) { umma::mbar_wait(&done_bar[s ^ 1], (done_ph >> (s ^ 1)) & 1u); done_ph ^= 1u << (s ^ 1); }
+                        load_item(i + 1);
+                    }
+                    umma::mbar_wait(&ld_bar[s], (ld_ph >> s) & 1u); ld_ph ^= 1u << s;
+                    const uint32_t sa = umma::smem_u32(smem_raw + (size_t)s * 2 * OPV), sz = sa + OPV;
+                    for (int tt = 0; tt < mt; tt++)
+                        umma::gemm_issue(tmem + tt * H, sa + tt * 16 * RV * 16, 128, RV * 16, 256, sz, 128, RV * 16, 256,
+                                         umma::idesc_bf16(128, H, 1, 1), RV / 16, i > 0 ? 1u : 0u);
+                    umma::mma_commit(&done_bar[s]);
+                }
+                // drain the done barriers so their phases stay in step for the next layer
+                if (cnt >= 2) { const int s2 = (cnt - 2) & 1; umma::mbar_wait(&done_bar[s2], (done_ph >> s2) & 1u); done_ph ^= 1u << s2; }
+                { const int s1 = (cnt - 1) & 1; umma::mbar_wait(&done_bar[s1], (done_ph >> s1) & 1u); done_ph ^= 1u << s1; }
+                umma::mma_commit(&mma_bar);
+            }
+            wait_mma();
+            drain_dw_to(part + nd.offW[l]);
+            __syncthreads();
+        }
+        if (tid == 0) { w_cur = -1; w_pending = false; }            // the stages overwrote the weight buffer
+    };
 
     const int total_tiles = args.sets[0].ntiles;
     float acc[NC][UT];
@@ -381,7 +458,7 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                     }
                 break;
             }
-            write_operand(bufZ, acc, true);
+            write_operand(bufZ, acc, !defer);
             // A_{l-1} (dW operand) recomputed from the stash
             {
                 const float* sp = stash + (size_t)(l - 2) * lstride + (size_t)j0 * TP + p;
@@ -401,7 +478,7 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                     }
                 }
             }
-            write_operand(bufA, acc, true);
+            write_operand(bufA, acc, !defer);
             umma::fence_async_smem();
             umma::tc_fence_before();
             __syncthreads();
@@ -415,29 +492,7 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                 issue_terms(tmem + da_off, z_addr + h * (HW / 8) * R * 16, R * 16, 128, 2 * R * 16, w_addr, H * 16, 128, 2 * H * 16,
                             wBytes, umma::idesc_bf16(128, H, 0, 0), HW / 16, h > 0 ? 1u : 0u);
             };
-            auto drain_dw = [&]() {                       // TMEM rows = fan-in index k, columns = unit j
-                umma::tc_fence_after();
-                float* dst = part + nd.offW[l];
-                for (int tt = 0; tt < mt; tt++) {
-                    if (tt * 128 + lg * 32 < H) {
-                        const int k = tt * 128 + lg * 32 + lane;
-                        const int c0 = wsub * (H / nsub);
-                        for (int c = c0; c < c0 + H / nsub; c += 16) {
-                            uint32_t r[16];
-                            umma::tmem_ld16_nowait(tmem + ((uint32_t)(lg * 32) << 16) + tt * H + c, r);
-                            umma::tmem_ld_wait();
-                            float4* d4 = reinterpret_cast<float4*>(dst + (size_t)k * H + c);
-                            if (k < H) {
-                                #pragma unroll
-                                for (int q = 0; q < 4; q++)     // 16-byte vector reduction, single owner per element
-                                    atomicAdd(d4 + q, make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
-                                                                  __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
-                            }
-                        }
-                    }
-                }
-                umma::tc_fence_before();
-            };
+            auto drain_dw = [&]() { drain_dw_to(part + nd.offW[l]); };
 
             if (da_separate) {
                 if (tid == 0) {
@@ -451,10 +506,22 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                 if (tid == 0 && l > 2) w_request(l - 1, 0);
                 drain_dw();
             } else {
-                if (tid == 0) { umma::tc_fence_after(); issue_dw(); umma::mma_commit(&mma_bar); }
-                wait_mma();
-                drain_dw();
-                __syncthreads();
+                if (defer) {
+                    // dW of this tile-layer is deferred: its two operands (valid rows only) go to the ring by TMA bulk store
+                    if (tid == 0) {
+                        uint8_t* slot = ring + ((size_t)(gcount * (L - 1) + (l - 2)) * 2) * OPV;
+                        for (int h8 = 0; h8 < H / 8; h8++) {
+                            umma::bulk_s2g(slot + (size_t)h8 * RV * 16, bufA + (size_t)h8 * R * 16, RV * 16);
+                            umma::bulk_s2g(slot + OPV + (size_t)h8 * RV * 16, bufZ + (size_t)h8 * R * 16, RV * 16);
+                        }
+                        umma::bulk_commit();
+                    }
+                } else {
+                    if (tid == 0) { umma::tc_fence_after(); issue_dw(); umma::mma_commit(&mma_bar); }
+                    wait_mma();
+                    drain_dw();
+                    __syncthreads();
+                }
                 for (int h = 0; h < nhalf; h++) {
                     if (tid == 0) {
                         umma::tc_fence_after();
@@ -469,10 +536,18 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                     }
                 }
             }
+            if (defer) {                                  // the staging area aliases the operands the bulk stores read
+                if (tid == 0) umma::bulk_wait_read_all();
+                __syncthreads();
+            }
             stage_to_regs(da_off, acc);                   // acc = Abar_{l-1}
+        }
+        if (defer && args.mode == 0) {
+            if (++gcount == ta.defer_g) { catch_up(gcount); gcount = 0; }
         }
     }
 
+    if (defer && gcount > 0) catch_up(gcount);
     umma::tc_fence_before();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, (uint32_t)ta.tmem_cols);
