@@ -203,7 +203,6 @@ struct pinn_ctx {
     tc_fn kern_tc = nullptr;
     __nv_bfloat16* d_wq = nullptr;
     long long wq_term_stride = 0;
-    int tc_shared_rows = 0;          // > 0: tensor-core CTAs share this many L2-resident partial rows (experiment knob)
     uint8_t* d_ring = nullptr; long long ring_per_cta = 0; int tc_defer_g = 0;   // deferred dW (width 256)
     int tc_ut = 8, nterms = 0, tc_threads = 0, tc_smem = 0, tc_tmem_cols = 0, grid_cap_tc = 0;
     AdamArgs adam{};
@@ -435,7 +434,6 @@ static int configure_kernels(pinn_ctx* c) {
         if (occ > tmem_limit) occ = tmem_limit;
         c->grid_cap_tc = occ * c->num_sms;
         c->kernel_id = 100 + nterms;
-        if (const char* e = getenv("PINN_TC_SHARED_ROWS")) c->tc_shared_rows = atoi(e);
         if (H == 256 && nterms == 1 && nd.L >= 2) {
             c->tc_defer_g = 16;
             if (const char* e = getenv("PINN_TC_DEFER")) c->tc_defer_g = atoi(e);
@@ -471,7 +469,6 @@ static int launch_fused(pinn_ctx* c, cudaStream_t stream, bool full, const Point
     for (int i = 0; i < nsets; i++) a.sets[i] = sets[i];
     a.partial = c->d_partial; a.stash = c->d_stash; a.row0 = row0; a.nsplit_cap = c->nsplit_cap;
     a.stash_per_cta = c->stash_per_cta;
-    a.part_rows = 0;
     a.mode = mode; a.y_out = y_out; a.r_out = r_out;
     const bool tc = full && c->kern_tc != nullptr;
     if (tc) {                                             // 16-point tiles on the tensor-core kernel
@@ -490,7 +487,6 @@ static int launch_fused(pinn_ctx* c, cudaStream_t stream, bool full, const Point
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, stream);
     }
-    if (tc && c->tc_shared_rows > 0) a.part_rows = c->tc_shared_rows;
     if (tc) {
         TcArgs ta{};
         ta.f = a; ta.wq = c->d_wq; ta.wq_term_stride = c->wq_term_stride; ta.tmem_cols = c->tc_tmem_cols;
@@ -504,7 +500,7 @@ static int launch_fused(pinn_ctx* c, cudaStream_t stream, bool full, const Point
     }
     if (timed) { cudaEventRecord(e1, stream); c->pending.emplace_back(e0, e1); }
     if (full) c->last_grid = grid;
-    if (grid_out) *grid_out = wk ? grid * c->warp_wpc : ((tc && a.part_rows > 0 && a.part_rows < grid) ? a.part_rows : grid);   // partial rows this launch used
+    if (grid_out) *grid_out = wk ? grid * c->warp_wpc : grid;   // partial rows this launch used
     c->step_launches++;
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
     return PINN_OK;

@@ -38,7 +38,6 @@ struct FusedArgs {
     float* partial;             // [rows][PP]: one row per CTA of every launch of the step
     float* stash;               // [rows][stash_per_cta]
     int row0;                   // first partial / stash row of this launch (launches of one step run concurrently)
-    int part_rows;              // > 0: CTAs share this many partial rows (row = blockIdx % part_rows; RED is atomic)
     int nsplit_cap;             // > 1: dW micro-tiles may split the tile columns, partials meet in smem scratch
     long long stash_per_cta;    // floats
     int mode;                   // 0 = train (loss + gradients), 1 = evaluate (y, r out)

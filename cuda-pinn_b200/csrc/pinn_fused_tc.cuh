@@ -74,7 +74,7 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
     constexpr int nwarps = (16 * H / UT) >> 5, nsub = nwarps >> 2;
     const int lg = warp & 3, wsub = warp >> 2;
     float* stash = args.stash + (size_t)(args.row0 + blockIdx.x) * args.stash_per_cta;
-    float* part = args.partial + (size_t)(args.row0 + (args.part_rows > 0 ? (int)(blockIdx.x % args.part_rows) : (int)blockIdx.x)) * nd.PP;
+    float* part = args.partial + (size_t)(args.row0 + blockIdx.x) * nd.PP;
     constexpr int lstride = NC * H * TP;
 
     if (warp == 0) umma::tmem_alloc(&tmem_slot, (uint32_t)ta.tmem_cols);
