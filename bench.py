@@ -184,6 +184,27 @@ def cpu_baseline(which, seconds=12.0):
             "sample": f"{pts} interior points x {steps} steps, oracle FP32 + OpenMP ({sec:.1f} s)"}
 
 
+def reference_cuda_composed(which):
+    """B-ref-cuda: the reference's own tensor<float> ops composing the interior part of the step
+    op by op (+ labelled host shim for tanh/sqrt), oracle/_ref/ref_step built from /root/reference.  Burgers nets only."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_step")
+    if which not in (1, 2) or not os.path.exists(exe):
+        return None
+    out = {}
+    for name, path, n, steps in (("O3", exe, 4096, 2), ("as_shipped_G", exe + "_dbg", 2048, 1)):
+        if not os.path.exists(path):
+            continue
+        try:
+            r = subprocess.run([path, str(n), "20", "8", str(steps)], capture_output=True, text=True, timeout=240)
+            kv = dict(l.split("=", 1) for l in r.stdout.splitlines() if "=" in l and not l.startswith("steps"))
+            out[name] = {"value": float(kv["points_per_second"]), "unit": "points/s",
+                         "sample": f"{n} interior points x {steps} steps (chunked: the reference mirrors every tensor on the host)"}
+        except Exception as e:   # noqa: BLE001
+            out[name] = {"error": str(e)[:200]}
+    out["what"] = "reference tensor<float> ops + host shim for tanh/sqrt; NOT the reference's train step (it has none)"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -344,6 +365,9 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(which)
+            rc = reference_cuda_composed(which)
+            if rc:
+                line["reference_cuda_composed"] = rc
         print(json.dumps(line), flush=True)
     net.close()
     if dist is not None:

@@ -86,3 +86,24 @@ def test_network_header_against_reference_tensor(oracle):
     ocfg = oracle.baseline_config(1)
     _, s_ref = oracle.loss_grad(ocfg, w.astype(np.float64), *[oracle.sample(ocfg, k) for k in range(3)], want_grad=False)
     assert float(kv["loss0"].split()[0]) == pytest.approx(oracle.loss_from_sums(ocfg, s_ref)[0], rel=1e-5)
+
+
+def test_reference_composed_step_matches_oracle_loss(oracle):
+    """oracle/_ref/ref_step: the reference's own tensor<float> ops (+ labelled host shim for tanh/sqrt) composing the
+    interior part of the train step.  Its loss must equal the oracle's residual MSE on the same points and weights —
+    this pins the oracle's math on the reference's matmul / broadcast / dot / transpose semantics end to end."""
+    out = subprocess.run([_ref(oracle, "ref_step"), "512", "20", "8", "1"], capture_output=True, text=True, check=True, timeout=600).stdout
+    kv = dict(line.split("=", 1) for line in out.strip().splitlines() if "=" in line and not line.startswith("steps"))
+    ocfg = oracle.make_config(oracle.PDE_BURGERS, 20, 8, 512, 1, 1)
+    xf = oracle.sample(ocfg, 0)
+    w = oracle.init_params(ocfg).astype(np.float64)
+    _, s = oracle.loss_grad(ocfg, w, xf, np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), want_grad=False)
+    assert float(kv["loss0"]) == pytest.approx(s[0] / 512, rel=2e-5)
+    # one Adam step on the same gradient lowers the interior loss the same way the oracle does
+    g, _ = oracle.loss_grad(ocfg, w, xf, np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32))
+    # the oracle's gradient includes the 2/N seed with N = n_interior, like ref_step
+    m = np.zeros_like(w); v = np.zeros_like(w); w1 = w.copy()
+    oracle.adam(ocfg, w1, m, v, g, 1)
+    _, s1 = oracle.loss_grad(ocfg, w1, xf, np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), want_grad=False)
+    assert float(kv["loss_last"]) == pytest.approx(s1[0] / 512, rel=1e-3)
+    assert float(kv["points_per_second"]) > 0
