@@ -55,6 +55,11 @@ def traffic_for(which, prec_name):
         return None
 
 
+def traffic_bytes(which, prec_name, points):
+    t = traffic_for(which, prec_name)
+    return None if not t else t["bytes_per_point"] * points
+
+
 def peaks():
     p = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0, "source": "fallback"}
     try:
@@ -343,7 +348,7 @@ def main():
             rf_kernel = "fused_step_fp32 (interior)"
         roofline = {
             "bound": rf_bound, "kernel": rf_kernel, "achieved": ach_tf, "peak": rf_peak,
-            "unit": "TFLOP/s", "frac": ach_tf / rf_peak, "traffic": traffic_for(which, prec_name),
+            "unit": "TFLOP/s", "frac": ach_tf / rf_peak, "traffic": traffic_bytes(which, prec_name, n_loc0), "traffic_source": (traffic_for(which, prec_name) or {}).get("source"),
             "peak_source": rf_src, "issued_tensor_tflops": ach_tf * mma_mult if tensor_path else 0.0,
             "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step if ms_step else None,
             "hbm": {"achieved": ach_gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_gb / pk["hbm_gbs"], "of": pk["source"]},
