@@ -278,3 +278,40 @@ def test_tensor_core_rejects_unsupported_widths(P, oracle):
     with pytest.raises(P.PinnError) as ei:
         P.Network(pcfg(P, ocfg, precision=2))
     assert ei.value.code == 7 and "width 64, 128 or 256" in str(ei.value)
+
+
+def test_deferred_dw_catch_up_over_several_groups(P, oracle):
+    """Width 256 defers dW: operands go to a ring, every 16 tiles a catch-up pass accumulates them in TMEM.  45,000
+    points = 2,813 tiles over 148 CTAs = 19 tiles per CTA: one full group of 16 and a tail of 3 per CTA."""
+    ocfg = oracle.make_config(oracle.PDE_ALLEN_CAHN, 256, 2, 45000, 256, 256)
+    xs = [oracle.sample(ocfg, k) for k in range(3)]
+    rng = np.random.default_rng(3)
+    w = (oracle.init_params(ocfg) + 0.02 * rng.standard_normal(oracle.num_params(ocfg))).astype(np.float32)
+    g_ref, s_ref = oracle.loss_grad(ocfg, w.astype(np.float64), *xs)
+    l_ref = oracle.loss_from_sums(ocfg, s_ref)[0]
+    res = []
+    for _ in range(2):
+        with P.Network(pcfg(P, ocfg, precision=2)) as net:
+            net.set_params(w)
+            out = net.loss_grad()
+            res.append(net.get_grads())
+    assert abs(out["loss"] / l_ref - 1) < 5e-3
+    assert rel_err(res[0], g_ref) < 1e-2
+    assert np.array_equal(res[0].view(np.uint32), res[1].view(np.uint32))       # private partial rows: bit-reproducible
+
+
+def test_warp_autonomous_kernel_opt_in(P, oracle, monkeypatch):
+    """PINN_WARP_KERNEL=1 selects fused_step_warp (kernel_id 50) for the 2->[20xL]->1 network; same parity bar."""
+    monkeypatch.setenv("PINN_WARP_KERNEL", "1")
+    ocfg = oracle.baseline_config(2, n_interior=25600 + 7)
+    with P.Network(pcfg(P, ocfg)) as net:
+        w = net.get_params()
+        out = net.loss_grad()
+        g = net.get_grads()
+        assert net.profile_get()["kernel_id"] == 50
+        losses = [net.train_step()["loss"] for _ in range(3)]
+    xs = [oracle.sample(ocfg, k) for k in range(3)]
+    g_ref, s_ref = oracle.loss_grad(ocfg, w.astype(np.float64), *xs)
+    assert abs(out["loss"] / oracle.loss_from_sums(ocfg, s_ref)[0] - 1) < 1e-5
+    assert rel_err(g, g_ref) < 1e-4
+    assert losses[0] == pytest.approx(out["loss"], rel=1e-6) and losses[2] < losses[0]
