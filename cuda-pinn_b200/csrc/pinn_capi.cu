@@ -200,7 +200,7 @@ struct pinn_ctx {
     long long stash_per_cta = 0;
     // tensor-core path (precision != FP32): interior set only
     typedef void (*tc_fn)(const NetDims, const TcArgs);
-    tc_fn kern_tc = nullptr;
+    tc_fn kern_tc = nullptr, kern_tc_val = nullptr;     // kern_tc_val: value-only tiles (boundary / initial sets)
     __nv_bfloat16* d_wq = nullptr;
     long long wq_term_stride = 0;
     uint8_t* d_ring = nullptr; long long ring_per_cta = 0; int tc_defer_g = 0;   // deferred dW (width 256)
@@ -419,6 +419,15 @@ static int configure_kernels(pinn_ctx* c) {
         else c->kern_tc = PICK_TC(3, 2);
 #undef PICK_TC
 #undef PICK_TC_H
+        // boundary / initial sets on the tensor cores too (128-point value-only tiles); PINN_TC_VAL=0 keeps them on FP32
+        const char* ev = getenv("PINN_TC_VAL");
+        if (!(ev && atoi(ev) == 0)) {
+#define PICK_TCV(D) (H == 64 ? (nterms == 2 ? fused_step_tc<D, 0, 2, 8, 64, true> : fused_step_tc<D, 0, 1, 8, 64, true>) \
+                   : (H == 128 ? (nterms == 2 ? fused_step_tc<D, 0, 2, 8, 128, true> : fused_step_tc<D, 0, 1, 8, 128, true>) \
+                               : fused_step_tc<D, 0, 1, 8, 256, true>))
+            c->kern_tc_val = nd.d_in == 2 ? PICK_TCV(2) : PICK_TCV(3);
+#undef PICK_TCV
+        }
         const int HW = H > 128 ? 128 : H;
         c->nterms = nterms;
         c->tc_threads = 16 * H / c->tc_ut;
@@ -427,6 +436,8 @@ static int configure_kernels(pinn_ctx* c) {
             return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: PINN_PREC_BF16X3 needs width <= 128 (operand terms do not fit in shared memory)");
         c->tc_tmem_cols = (H == 256) ? 512 : 2 * H;
         CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, c->tc_smem));
+        if (c->kern_tc_val)
+            CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_tc_val, cudaFuncAttributeMaxDynamicSharedMemorySize, c->tc_smem));
         int occ = 0;
         CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->kern_tc, c->tc_threads, c->tc_smem));
         if (occ < 1) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: tensor-core kernel does not fit on an SM");
@@ -470,13 +481,15 @@ static int launch_fused(pinn_ctx* c, cudaStream_t stream, bool full, const Point
     a.partial = c->d_partial; a.stash = c->d_stash; a.row0 = row0; a.nsplit_cap = c->nsplit_cap;
     a.stash_per_cta = c->stash_per_cta;
     a.mode = mode; a.y_out = y_out; a.r_out = r_out;
-    const bool tc = full && c->kern_tc != nullptr;
-    if (tc) {                                             // 16-point tiles on the tensor-core kernel
+    const bool tcv = !full && mode == 0 && c->kern_tc_val != nullptr;      // value-only tiles of 128 points
+    const bool tc = (full && c->kern_tc != nullptr) || tcv;
+    if (tc) {                                             // 16-point (value-only: 128-point) tiles on the tensor-core kernel
         total = 0;
-        for (int i = 0; i < nsets; i++) { a.sets[i].ntiles = tiles_of(a.sets[i].n, 16); total += a.sets[i].ntiles; }
+        for (int i = 0; i < nsets; i++) { a.sets[i].ntiles = tiles_of(a.sets[i].n, tcv ? 128 : 16); total += a.sets[i].ntiles; }
     }
     const bool wk = full && mode == 0 && !tc && c->kern_warp != nullptr;
     const int cap = tc ? c->grid_cap_tc : (full ? c->grid_cap_full : c->grid_cap_val);
+    (void)tcv;
     int grid = total < cap ? total : cap;
     if (wk) {                                             // one warp per 32-point tile, WPC warps per CTA, one CTA per SM
         grid = total < c->num_sms ? total : c->num_sms;        // spread tiles over the SMs first, then over warps
@@ -490,8 +503,8 @@ static int launch_fused(pinn_ctx* c, cudaStream_t stream, bool full, const Point
     if (tc) {
         TcArgs ta{};
         ta.f = a; ta.wq = c->d_wq; ta.wq_term_stride = c->wq_term_stride; ta.tmem_cols = c->tc_tmem_cols;
-        ta.op_ring = c->d_ring; ta.ring_per_cta = c->ring_per_cta; ta.defer_g = (mode == 0) ? c->tc_defer_g : 0;
-        c->kern_tc<<<grid, c->tc_threads, c->tc_smem, stream>>>(c->nd, ta);
+        ta.op_ring = c->d_ring; ta.ring_per_cta = c->ring_per_cta; ta.defer_g = (mode == 0 && !tcv) ? c->tc_defer_g : 0;
+        (tcv ? c->kern_tc_val : c->kern_tc)<<<grid, c->tc_threads, c->tc_smem, stream>>>(c->nd, ta);
     } else if (wk) {
         c->kern_warp<<<grid, c->warp_wpc * 32, c->warp_smem, stream>>>(c->nd, a);
     } else {
@@ -708,10 +721,11 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     c->rows_cap_a = c->grid_cap_full > c->grid_cap_tc ? c->grid_cap_full : c->grid_cap_tc;
     if (c->grid_cap_val > c->rows_cap_a) c->rows_cap_a = c->grid_cap_val;      // pinn_forward uses the value kernel on rows A
     if (c->kern_warp && c->num_sms * c->warp_wpc > c->rows_cap_a) c->rows_cap_a = c->num_sms * c->warp_wpc;
-    c->rows_cap_b = c->grid_cap_val;
+    c->rows_cap_b = c->grid_cap_val > c->grid_cap_tc ? c->grid_cap_val : c->grid_cap_tc;
     const size_t nrows = (size_t)c->rows_cap_a + c->rows_cap_b;
     c->stash_per_cta = (long long)nd.L * nd.C * nd.H * c->TP;   // the tensor-core kernel (16-point tiles) needs no more
     if ((long long)nd.L * nd.H * c->val_TP > c->stash_per_cta) c->stash_per_cta = (long long)nd.L * nd.H * c->val_TP;
+    if (c->kern_tc_val && (long long)nd.L * 8 * nd.H * 16 > c->stash_per_cta) c->stash_per_cta = (long long)nd.L * 8 * nd.H * 16;
     const size_t P = nd.P;
     TRY_C(cudaMalloc(&c->d_params, (P + 4) * sizeof(float)));     // +4: kernels copy them in float4 units
     TRY_C(cudaMalloc(&c->d_paramsT, (P + 4) * sizeof(float)));

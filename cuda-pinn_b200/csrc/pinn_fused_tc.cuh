@@ -46,12 +46,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // UT = units per thread (8: one 16-byte operand chunk per channel, 2H threads; 4: half a chunk,
 // 4H threads at <= 64 registers — twice the resident warps to hide the serialized phase latencies).
 // HT: hidden width fixed at compile time (64 / 128 / 256): offsets fold to immediates.
-template <int DIN, int N2, int NTERMS, int UT, int HT>
+// VAL: value-channel-only tiles for the boundary / initial sets.  The NC "channels" of a tile are then 8
+// independent groups of 16 points (row m = c*16 + p is point base + c*16 + p): 128 points fill the UMMA tile,
+// the elementwise work is a plain tanh per row, and the loss is the Dirichlet / initial target misfit.
+template <int DIN, int N2, int NTERMS, int UT, int HT, bool VAL = false>
 __global__ void __launch_bounds__(16 * HT / UT, 512 / (16 * HT / UT))
 fused_step_tc(const NetDims nd, const TcArgs ta) {
-    constexpr int NC = 1 + DIN + N2, TP = 16, R = 128;
+    constexpr int NC = VAL ? 8 : 1 + DIN + N2, TP = 16, R = 128;
     static_assert(UT == 8 || UT == 4, "unit group of 4 or 8");
-    constexpr int LD = NC * TP + 2;                   // staging leading dimension (floats)
+    constexpr int LD = VAL ? NC * TP : NC * TP + 2;   // staging leading dimension (floats); VAL: 128 rows fill the
+                                                      // aliased operand buffers exactly (H * 512 B), so no padding there
     constexpr int RV = NC * TP;                       // valid rows of the 128-row tile
     const FusedArgs& args = ta.f;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -180,7 +184,7 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
 
     // ---- deferred dW (see TcArgs) ----
     constexpr uint32_t OPV = (uint32_t)(H / 8) * RV * 16;          // one stored operand: valid rows only
-    const bool defer = (!da_separate) && ta.defer_g > 0 && NTERMS == 1;
+    const bool defer = (!da_separate) && ta.defer_g > 0 && NTERMS == 1 && !VAL;   // VAL tiles have 128 valid rows: stages would not fit
     uint8_t* ring = ta.op_ring + (size_t)blockIdx.x * ta.ring_per_cta;
     int gcount = 0;                                                 // tiles stored since the last catch-up
     uint32_t ld_ph = 0, done_ph = 0;                                // phase bits of ld_bar[s] / done_bar[s] (thread 0)
@@ -245,22 +249,51 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
         if (tid == 0) { w_cur = -1; w_pending = false; }            // the stages overwrote the weight buffer
     };
 
-    const int total_tiles = args.sets[0].ntiles;
+    const int total_tiles = args.sets[0].ntiles + ((VAL && args.nsets > 1) ? args.sets[1].ntiles : 0);
+    constexpr int PPT = VAL ? NC * TP : TP;               // points per tile
     float acc[NC][UT];
 
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const PointSet ps = args.sets[0];
-        const unsigned long long base = (unsigned long long)t * TP;
-        const bool valid = base + p < ps.n;
+        const int si = (VAL && t >= args.sets[0].ntiles) ? 1 : 0;
+        const PointSet ps = args.sets[si];
+        const unsigned long long base = (unsigned long long)(t - (si ? args.sets[0].ntiles : 0)) * PPT;
+        const bool valid = base + p < ps.n;               // (VAL: validity is per point group, see vpt())
+        auto vpt = [&](int c) { return base + (unsigned long long)(c * TP + p) < ps.n; };
         float x[3] = {0.0f, 0.0f, 0.0f};
-        if (valid) {
+        if (!VAL && valid) {
             #pragma unroll
             for (int k = 0; k < DIN; k++) x[k] = __ldg(ps.x + (base + p) * DIN + k);
         }
+        auto xval = [&](int c, int k) -> float {          // VAL: coordinate k of this thread's point in group c
+            return vpt(c) ? __ldg(ps.x + (base + c * TP + p) * DIN + k) : 0.0f;
+        };
         if (tid == 0 && L >= 2) w_request(2, 0);
 
         // ---------------- layer 1 (K = d_in): CUDA cores ----------------
-        {
+        if constexpr (VAL) {
+            const float* W1 = args.params + nd.offW[1];
+            float* st = stash + (size_t)j0 * TP + p;
+            float xc[NC][DIN];
+            #pragma unroll
+            for (int c = 0; c < NC; c++)
+                #pragma unroll
+                for (int k = 0; k < DIN; k++) xc[c][k] = xval(c, k);
+            #pragma unroll
+            for (int u = 0; u < UT; u++) {
+                const float b1 = __ldg(args.params + nd.offB[1] + j0 + u);
+                float w1[DIN];
+                #pragma unroll
+                for (int k = 0; k < DIN; k++) w1[k] = __ldg(W1 + k * H + j0 + u);
+                #pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    float z0 = b1;
+                    #pragma unroll
+                    for (int k = 0; k < DIN; k++) z0 = fmaf(xc[c][k], w1[k], z0);
+                    const float a = tanhf(z0);
+                    st[(size_t)(c * H + u) * TP] = a; acc[c][u] = a;
+                }
+            }
+        } else {
             const float* W1 = args.params + nd.offW[1];
             float* st = stash + (size_t)j0 * TP + p;
             #pragma unroll
@@ -308,6 +341,17 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
             }
             stage_to_regs(0u, acc);
             float* st = stash + (size_t)(l - 1) * lstride + (size_t)j0 * TP + p;
+            if constexpr (VAL) {
+                #pragma unroll
+                for (int u = 0; u < UT; u++) {
+                    const float bl = __ldg(args.params + nd.offB[l] + j0 + u);
+                    #pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        const float a = tanhf(acc[c][u] + bl);
+                        st[(size_t)(c * H + u) * TP] = a; acc[c][u] = a;
+                    }
+                }
+            } else
             #pragma unroll
             for (int u = 0; u < UT; u++) {
                 const float a = tanhf(acc[0][u] + __ldg(args.params + nd.offB[l] + j0 + u));
@@ -356,11 +400,29 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                 for (int c = 0; c < NC; c++) {
                     float s = 0.0f;
                     for (int gg = 0; gg < G; gg++) s += xbuf[((gg * 3 + o) * NC + c) * TP + p];
-                    if (c == 0 && o < nd.d_out) s += __ldg(args.params + nd.offB[L + 1] + o);
+                    if ((VAL || c == 0) && o < nd.d_out) s += __ldg(args.params + nd.offB[L + 1] + o);
                     y[o][c] = (o < nd.d_out) ? s : 0.0f;
                 }
-            float ss = pde_residual<NC>(nd, x, y, ps.scale, ybar, r);
-            if (args.mode == 1) {
+            float ss = 0.0f;
+            if constexpr (VAL) {                          // every "channel" is a point: target misfit per point
+                #pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    float xc[3] = {0.0f, 0.0f, 0.0f}, gt[3] = {0.0f, 0.0f, 0.0f};
+                    #pragma unroll
+                    for (int k = 0; k < DIN; k++) xc[k] = xval(c, k);
+                    pde_target(nd, ps.set, xc, gt);
+                    const bool ok = vpt(c);
+                    #pragma unroll
+                    for (int o = 0; o < 3; o++) {
+                        const float e = (ok && o < nd.d_out) ? y[o][c] - gt[o] : 0.0f;
+                        ss += e * e;
+                        ybar[o][c] = ps.scale * e;
+                    }
+                }
+            } else {
+                ss = pde_residual<NC>(nd, x, y, ps.scale, ybar, r);
+            }
+            if (!VAL && args.mode == 1) {
                 if (valid) {
                     for (int o = 0; o < nd.d_out; o++)
                         #pragma unroll
@@ -369,7 +431,7 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                         for (int q = 0; q < nd.n_res; q++) args.r_out[(base + p) * nd.n_res + q] = r[q];
                 }
             } else {
-                if (!valid) {
+                if (!VAL && !valid) {
                     ss = 0.0f;
                     #pragma unroll
                     for (int o = 0; o < 3; o++)
@@ -380,7 +442,12 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                 for (int o = 0; o < 3; o++) {
                     #pragma unroll
                     for (int c = 0; c < NC; c++) ybuf[(o * NC + c) * TP + p] = ybar[o][c];
-                    const float sb = lane_group_sum<TP>(ybar[o][0]);
+                    float bsum = ybar[o][0];              // bias gradient: value channel (VAL: every row is one)
+                    if constexpr (VAL) {
+                        #pragma unroll
+                        for (int c = 1; c < NC; c++) bsum += ybar[o][c];
+                    }
+                    const float sb = lane_group_sum<TP>(bsum);
                     if (p == 0 && o < nd.d_out) red_add(part + nd.offB[L + 1] + o, sb);
                 }
                 const float sl = lane_group_sum<TP>(ss);
@@ -423,6 +490,20 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
         for (int l = L; l >= 1; l--) {
             // adjoint of the tanh layer, in place: acc = Abar_l -> Zbar_l
             const float* st = stash + (size_t)(l - 1) * lstride + (size_t)j0 * TP + p;
+            if constexpr (VAL) {
+                #pragma unroll
+                for (int u = 0; u < UT; u++) {
+                    float bsum = 0.0f;
+                    #pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        const float a = st[(size_t)(c * H + u) * TP];
+                        const float zb = (1.0f - a * a) * acc[c][u];
+                        acc[c][u] = zb; bsum += zb;
+                    }
+                    const float sb = lane_group_sum<TP>(bsum);
+                    if (p == 0) red_add(part + nd.offB[l] + j0 + u, sb);
+                }
+            } else
             #pragma unroll
             for (int u = 0; u < UT; u++) {
                 const float a = st[(size_t)u * TP];
@@ -449,19 +530,42 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
             }
             if (l == 1) {
                 // dW_1[k][j] = sum_p ( x_k * zbar_0 + zbar_{1+k} )   (inputs: value x, unit tangents)
-                #pragma unroll
-                for (int u = 0; u < UT; u++)
+                if constexpr (VAL) {
                     #pragma unroll
                     for (int k = 0; k < DIN; k++) {
-                        const float s = lane_group_sum<TP>(fmaf(x[k], acc[0][u], acc[1 + k][u]));
-                        if (p == 0) red_add(part + nd.offW[1] + k * H + j0 + u, s);
+                        float xk[NC];
+                        #pragma unroll
+                        for (int c = 0; c < NC; c++) xk[c] = xval(c, k);
+                        #pragma unroll
+                        for (int u = 0; u < UT; u++) {
+                            float sx = 0.0f;
+                            #pragma unroll
+                            for (int c = 0; c < NC; c++) sx = fmaf(xk[c], acc[c][u], sx);
+                            const float s = lane_group_sum<TP>(sx);
+                            if (p == 0) red_add(part + nd.offW[1] + k * H + j0 + u, s);
+                        }
                     }
+                } else {
+                    #pragma unroll
+                    for (int u = 0; u < UT; u++)
+                        #pragma unroll
+                        for (int k = 0; k < DIN; k++) {
+                            const float s = lane_group_sum<TP>(fmaf(x[k], acc[0][u], acc[1 + k][u]));
+                            if (p == 0) red_add(part + nd.offW[1] + k * H + j0 + u, s);
+                        }
+                }
                 break;
             }
             write_operand(bufZ, acc, !defer);
             // A_{l-1} (dW operand) recomputed from the stash
             {
                 const float* sp = stash + (size_t)(l - 2) * lstride + (size_t)j0 * TP + p;
+                if constexpr (VAL) {
+                    #pragma unroll
+                    for (int u = 0; u < UT; u++)
+                        #pragma unroll
+                        for (int c = 0; c < NC; c++) acc[c][u] = sp[(size_t)(c * H + u) * TP];
+                } else
                 #pragma unroll
                 for (int u = 0; u < UT; u++) {
                     const float a = sp[(size_t)u * TP];
