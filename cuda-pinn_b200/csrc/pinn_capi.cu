@@ -645,8 +645,7 @@ static int step_once(pinn_ctx* c) {
 
 static int read_out(pinn_ctx* c, pinn_step_out* out) {
     if (!out) return PINN_OK;
-    CUDA_TRY(c, "pinn_train_step", cudaMemcpyAsync(c->h_pinned, c->d_loss, 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, "pinn_train_step", cudaMemcpyAsync(c->h_pinned + 4, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, "pinn_train_step", cudaMemcpyAsync(c->h_pinned, c->d_loss, 5 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, "pinn_train_step", cudaStreamSynchronize(c->stream));
     out->loss = c->h_pinned[0]; out->mse_residual = c->h_pinned[1];
     out->mse_boundary = c->h_pinned[2]; out->mse_initial = c->h_pinned[3];
@@ -741,17 +740,16 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
         TRY_C(cudaMalloc(&c->d_wq, (size_t)c->nterms * c->wq_term_stride * sizeof(__nv_bfloat16)));
     }
     if (c->tc_defer_g > 0) TRY_C(cudaMalloc(&c->d_ring, (size_t)c->grid_cap_tc * c->ring_per_cta));
-    TRY_C(cudaMalloc(&c->d_loss, 4 * sizeof(float)));
+    TRY_C(cudaMalloc(&c->d_loss, 8 * sizeof(float)));          // [0..3] loss record, [4] overflow flag word: one D2H copy per read-back
     TRY_C(cudaMalloc(&c->d_step, sizeof(unsigned long long)));
-    TRY_C(cudaMalloc(&c->d_flag, sizeof(int)));
+    c->d_flag = reinterpret_cast<int*>(c->d_loss + 4);
     TRY_C(cudaMallocHost(&c->h_pinned, 8 * sizeof(float)));
     TRY_C(cudaMemsetAsync(c->d_m, 0, P * sizeof(float), c->stream));
     TRY_C(cudaMemsetAsync(c->d_v, 0, P * sizeof(float), c->stream));
     TRY_C(cudaMemsetAsync(c->d_gbuf, 0, (size_t)nd.PP * sizeof(float), c->stream));
     TRY_C(cudaMemsetAsync(c->d_partial, 0, nrows * nd.PP * sizeof(float), c->stream));
-    TRY_C(cudaMemsetAsync(c->d_loss, 0, 4 * sizeof(float), c->stream));
+    TRY_C(cudaMemsetAsync(c->d_loss, 0, 8 * sizeof(float), c->stream));
     TRY_C(cudaMemsetAsync(c->d_step, 0, sizeof(unsigned long long), c->stream));
-    TRY_C(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
 #undef TRY_C
     std::vector<float> w;
     host_init_params(nd, cfg->seed_weights, w);
@@ -773,7 +771,7 @@ void pinn_destroy(pinn_ctx* c) {
     for (int k = 0; k < 3; k++) cudaFree(c->d_x[k]);
     cudaFree(c->d_params); cudaFree(c->d_paramsT); cudaFree(c->d_m); cudaFree(c->d_v);
     cudaFree(c->d_gbuf); cudaFree(c->d_partial); cudaFree(c->d_stash); cudaFree(c->d_loss);
-    cudaFree(c->d_step); cudaFree(c->d_flag); cudaFree(c->d_wq); cudaFree(c->d_ring);
+    cudaFree(c->d_step); cudaFree(c->d_wq); cudaFree(c->d_ring);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     drop_graph(c);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
