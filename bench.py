@@ -265,6 +265,12 @@ def main():
         box = [P.Network.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         net.comm_init(box[0])
+        collective = "nccl all-reduce of [P+3] floats"
+        if os.environ.get("PINN_P2P", "1") != "0":
+            hs = [None] * world
+            dist.all_gather_object(hs, net.p2p_export())
+            net.p2p_open(hs)
+            collective = "fused reduce + peer-memory all-reduce + Adam kernel (NVLink P2P, IPC-mapped exchange buffers)"
     stream = torch.cuda.ExternalStream(net.stream(), device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
@@ -363,7 +369,7 @@ def main():
             "dtype": {"fp32": "f32", "bf16x3": "bf16x3 operands (2-term split), f32 accumulate + f32 elementwise",
                       "bf16": "bf16 operands, f32 accumulate + f32 elementwise"}[prec_name], "data": "synthetic",
             "config": {"workload": CONFIG_NAMES[which], "precision": prec_name, "points_per_gpu": per_gpu, "n_interior": nf, "n_boundary": nb,
-                       "n_initial": n0, "parallelism": f"dp{world}", "l2": "flushed (256 MiB memset) between timed steps",
+                       "n_initial": n0, "parallelism": f"dp{world}", "collective": collective if world > 1 else None, "l2": "flushed (256 MiB memset) between timed steps",
                        "kernel_id": prof["kernel_id"], "grid": prof["grid"], "block": prof["block"], "smem": prof["smem_bytes"]},
             "roofline": roofline, "e2e": e2e, "gpu_launches": prof["launches"], "clocks": clocks,
             "final_loss": last["loss"], "wall_s": wall,

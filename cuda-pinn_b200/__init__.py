@@ -55,7 +55,7 @@ ABI_SYMBOLS = [
     "pinn_sample_points", "pinn_resample_points", "pinn_set_points", "pinn_get_points", "pinn_local_count",
     "pinn_train_step", "pinn_train_step_host", "pinn_train_steps", "pinn_loss_grad",
     "pinn_forward", "pinn_residual", "pinn_synchronize",
-    "pinn_comm_unique_id", "pinn_comm_init", "pinn_step_local", "pinn_step_apply",
+    "pinn_comm_unique_id", "pinn_comm_init", "pinn_comm_p2p_export", "pinn_comm_p2p_open", "pinn_step_local", "pinn_step_apply",
     "pinn_grad_buffer", "pinn_stream", "pinn_profile_enable", "pinn_profile_get",
 ]
 
@@ -106,6 +106,8 @@ def lib():
     L.pinn_synchronize.argtypes = [vp]
     L.pinn_comm_unique_id.argtypes = [vp]
     L.pinn_comm_init.argtypes = [vp, vp]
+    L.pinn_comm_p2p_export.argtypes = [vp, vp]
+    L.pinn_comm_p2p_open.argtypes = [vp, vp, C.c_int]
     L.pinn_step_local.argtypes = [vp]
     L.pinn_step_apply.argtypes = [vp, P(PinnStepOut)]
     L.pinn_grad_buffer.argtypes = [vp, P(C.c_size_t)]; L.pinn_grad_buffer.restype = vp
@@ -283,6 +285,18 @@ class Network:
     def comm_init(self, id_bytes):
         buf = (C.c_char * 128).from_buffer_copy(id_bytes)
         self._check(self._L.pinn_comm_init(self._h, buf))
+
+    def p2p_export(self):
+        """IPC handle (64 bytes) of this rank's exchange buffer for the fused peer-memory all-reduce."""
+        buf = (C.c_char * 64)()
+        self._check(self._L.pinn_comm_p2p_export(self._h, buf))
+        return bytes(buf)
+
+    def p2p_open(self, handles):
+        """handles: list of the 64-byte IPC handles of ALL ranks in rank order."""
+        blob = b"".join(handles)
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        self._check(self._L.pinn_comm_p2p_open(self._h, buf, len(handles)))
 
     def grad_buffer(self):
         n = C.c_size_t()

@@ -77,32 +77,18 @@ struct AdamArgs {
     double inv_nf, inv_nb, inv_n0;
 };
 
-// Adam on the flat parameter vector + refresh of the transposed copy.
-__global__ void adam_kernel(const NetDims nd, const AdamArgs a, float* __restrict__ params,
-                            float* __restrict__ paramsT, float* __restrict__ m, float* __restrict__ v,
-                            const float* __restrict__ gbuf, const unsigned long long* __restrict__ step,
-                            float* __restrict__ loss_out, int* __restrict__ flag, int apply) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) {
-        const float mr = (float)((double)gbuf[nd.P + 0] * a.inv_nf);
-        const float mb = (float)((double)gbuf[nd.P + 1] * a.inv_nb);
-        const float m0 = (float)((double)gbuf[nd.P + 2] * a.inv_n0);
-        const float loss = a.lambda_r * mr + a.lambda_b * mb + a.lambda_0 * m0;
-        loss_out[0] = loss; loss_out[1] = mr; loss_out[2] = mb; loss_out[3] = m0;
-        if (!isfinite(loss)) *flag = PINN_ERR_DEVICE_OVERFLOW;   // reference runtime.cuh error channel
-    }
-    if (i >= nd.P || !apply) return;
-    const double t = (double)(*step);
+// Adam for parameter i + refresh of the transposed mirror W^T[l] ([fan_out, fan_in]).
+__device__ __forceinline__ void adam_one(const NetDims& nd, const AdamArgs& a, float* __restrict__ params,
+                                         float* __restrict__ paramsT, float* __restrict__ m, float* __restrict__ v,
+                                         float g, double t, int i) {
     const float c1 = (float)(1.0 / (1.0 - pow((double)a.beta1, t)));
     const float c2 = (float)(1.0 / (1.0 - pow((double)a.beta2, t)));
-    const float g = gbuf[i];
     const float mi = a.beta1 * m[i] + (1.0f - a.beta1) * g;
     const float vi = a.beta2 * v[i] + (1.0f - a.beta2) * (g * g);
     m[i] = mi; v[i] = vi;
     const float mh = mi * c1, vh = vi * c2;
     const float w = params[i] - a.lr * (mh / (sqrtf(vh) + a.eps));
     params[i] = w;
-    // transposed mirror W^T[l] ([fan_out, fan_in]) used by the dA contraction
     int l = 1;
     while (l <= nd.L && i >= nd.offW[l + 1]) l++;
     const int fi = nd.fan_in(l), fo = nd.fan_out(l);
@@ -111,6 +97,137 @@ __global__ void adam_kernel(const NetDims nd, const AdamArgs a, float* __restric
         paramsT[nd.offW[l] + j * fi + k] = w;
     } else {
         paramsT[i] = w;
+    }
+}
+
+__device__ __forceinline__ void loss_record(const NetDims& nd, const AdamArgs& a, float sr, float sb, float s0,
+                                            float* __restrict__ loss_out, int* __restrict__ flag) {
+    const float mr = (float)((double)sr * a.inv_nf);
+    const float mb = (float)((double)sb * a.inv_nb);
+    const float m0 = (float)((double)s0 * a.inv_n0);
+    const float loss = a.lambda_r * mr + a.lambda_b * mb + a.lambda_0 * m0;
+    loss_out[0] = loss; loss_out[1] = mr; loss_out[2] = mb; loss_out[3] = m0;
+    if (!isfinite(loss)) *flag = PINN_ERR_DEVICE_OVERFLOW;       // reference runtime.cuh error channel
+}
+
+__global__ void adam_kernel(const NetDims nd, const AdamArgs a, float* __restrict__ params,
+                            float* __restrict__ paramsT, float* __restrict__ m, float* __restrict__ v,
+                            const float* __restrict__ gbuf, const unsigned long long* __restrict__ step,
+                            float* __restrict__ loss_out, int* __restrict__ flag, int apply) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) loss_record(nd, a, gbuf[nd.P + 0], gbuf[nd.P + 1], gbuf[nd.P + 2], loss_out, flag);
+    if (i >= nd.P || !apply) return;
+    adam_one(nd, a, params, paramsT, m, v, gbuf[i], (double)(*step), i);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused gradient reduction + all-reduce + Adam over NVLink peer memory (one kernel per rank per step).
+//   1. fixed-order sum of this GPU's CTA partial rows (as reduce_partials_kernel) into this rank's
+//      exchange buffer (IPC-mapped into every peer), parity = sequence number & 1;
+//   2. the last block to finish publishes the sequence number in the buffer's flag word
+//      (threadfence_system + release store);
+//   3. every block waits until every peer's flag has reached the sequence number (acquire loads over
+//      NVLink, bounded spin), then sums the R exchange buffers in RANK ORDER with cache-volatile peer
+//      loads — every rank adds the same numbers in the same order, so the weights stay bit-identical;
+//   4. Adam on the summed gradient, loss record.
+// Replaces reduce kernel + ncclAllReduce + Adam kernel; the payload is P+3 floats (12 KB .. 1.8 MB).
+// Double buffering by parity + the flag protocol make a buffer reusable: a rank can only overwrite
+// parity q again after every peer has published the step in between, i.e. has finished reading q.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxP2PRanks = 16;
+constexpr int kXchgHeader = 32;                         // floats reserved in front of the two payload slots
+struct P2PArgs {
+    float* peers[kMaxP2PRanks];                          // exchange buffers in rank order (own included)
+    int nranks, rank;
+    unsigned long long seq;                              // monotonic over the life of the communicator
+    unsigned int* done_counter;                          // local, zero between launches
+    int* err_flag;                                       // local: set when a peer never showed up
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(1024)
+reduce_exchange_adam_kernel(const NetDims nd, const AdamArgs a, float* __restrict__ part_a, int rows_a,
+                            float* __restrict__ part_b, int rows_b, float* __restrict__ params,
+                            float* __restrict__ paramsT, float* __restrict__ m, float* __restrict__ v,
+                            float* __restrict__ gbuf, unsigned long long* __restrict__ step, unsigned long long tstep,
+                            float* __restrict__ loss_out, int* __restrict__ flag, const P2PArgs x) {
+    __shared__ float part[32][33];
+    constexpr int RU = 8;
+    const int PP = nd.PP, n_out = nd.P + 3;
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.0f;
+    if (col < n_out) {
+        auto sum_rows = [&](const float* __restrict__ base, int rows) {
+            for (int r0 = threadIdx.y; r0 < rows; r0 += 32 * RU) {
+                float vv[RU];
+                #pragma unroll
+                for (int u = 0; u < RU; u++) {
+                    const int r = r0 + 32 * u;
+                    vv[u] = (r < rows) ? __ldcg(base + (size_t)r * PP + col) : 0.0f;
+                }
+                #pragma unroll
+                for (int u = 0; u < RU; u++) s += vv[u];
+            }
+        };
+        sum_rows(part_a, rows_a);
+        sum_rows(part_b, rows_b);
+        for (int r = threadIdx.y; r < rows_a; r += 32) part_a[(size_t)r * PP + col] = 0.0f;
+        for (int r = threadIdx.y; r < rows_b; r += 32) part_b[(size_t)r * PP + col] = 0.0f;
+    }
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    const int par = (int)(x.seq & 1ULL);
+    if (threadIdx.y == 0 && col < n_out) {
+        float t = 0.0f;
+        #pragma unroll
+        for (int y = 0; y < 32; y++) t += part[y][threadIdx.x];
+        x.peers[x.rank][kXchgHeader + (size_t)par * PP + col] = t;      // this rank's local sum, visible to the peers
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence_system();
+        const unsigned int old = atomicAdd(x.done_counter, 1u);
+        if (old == gridDim.x - 1) {                                    // every block of this rank has written its columns
+            *x.done_counter = 0u;
+            __threadfence_system();
+            st_release_sys(reinterpret_cast<unsigned long long*>(x.peers[x.rank]), x.seq);
+            *step = tstep;
+        }
+        const long long t0 = clock64();
+        for (int r = 0; r < x.nranks; r++) {
+            if (r == x.rank) continue;
+            const unsigned long long* pf = reinterpret_cast<const unsigned long long*>(x.peers[r]);
+            while (ld_acquire_sys(pf) < x.seq) {
+                if (clock64() - t0 > 4000000000LL) { *x.err_flag = PINN_ERR_NCCL; break; }   // ~2 s: peer never arrived
+                __nanosleep(200);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.y == 0 && col < n_out) {
+        float g = 0.0f;
+        for (int r = 0; r < x.nranks; r++) g += __ldcv(x.peers[r] + kXchgHeader + (size_t)par * PP + col);   // rank order
+        gbuf[col] = g;
+        if (col < nd.P) {
+            adam_one(nd, a, params, paramsT, m, v, g, (double)tstep, col);
+        } else if (col == nd.P) {
+            float s3[3];
+            #pragma unroll
+            for (int q = 0; q < 3; q++) {
+                float t = 0.0f;
+                for (int r = 0; r < x.nranks; r++) t += __ldcv(x.peers[r] + kXchgHeader + (size_t)par * PP + nd.P + q);
+                s3[q] = t;
+            }
+            loss_record(nd, a, s3[0], s3[1], s3[2], loss_out, flag);
+        }
     }
 }
 
@@ -207,13 +324,16 @@ struct pinn_ctx {
     int tc_ut = 8, nterms = 0, tc_threads = 0, tc_smem = 0, tc_tmem_cols = 0, grid_cap_tc = 0;
     AdamArgs adam{};
     void* comm = nullptr;
+    // peer-memory exchange (fused reduce + all-reduce + Adam)
+    float* d_xchg = nullptr; float* peer_ptr[kMaxP2PRanks] = {nullptr}; bool p2p_ready = false;
+    unsigned long long xseq = 0; unsigned int* d_done = nullptr;
     std::string err;
     // profiling
     bool prof = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
     double kernel_ms = 0.0; uint64_t kernel_count = 0, launches = 0;
-    int last_grid = 0;
+    int last_grid = 0, rows_a = 0, rows_b = 0;        // partial rows the last interior / boundary launches used
     uint64_t host_step = 0;
 };
 
@@ -521,7 +641,7 @@ static int launch_fused(pinn_ctx* c, cudaStream_t stream, bool full, const Point
 
 // Local part of a step: interior launch on the main stream, boundary + initial launch concurrently
 // on the auxiliary stream (disjoint partial rows), then the fixed-order reduction of all rows.
-static int run_local(pinn_ctx* c, int bump_step) {
+static int run_local(pinn_ctx* c, int bump_step, bool do_reduce = true) {
     PointSet v[2]; int nv = 0;
     for (int k = 1; k <= 2; k++) {
         if (c->n_local[k] == 0) continue;
@@ -544,10 +664,31 @@ static int run_local(pinn_ctx* c, int bump_step) {
         CUDA_TRY(c, "pinn_train_step", cudaEventRecord(c->ev_join, c->stream2));
         CUDA_TRY(c, "pinn_train_step", cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     }
+    c->rows_a = grid_a; c->rows_b = grid_b;
+    if (!do_reduce) return PINN_OK;
     const int n_out = c->nd.P + 3;
     reduce_partials_kernel<<<(n_out + 31) / 32, dim3(32, 32), 0, c->stream>>>(
         c->d_partial, grid_a, c->d_partial + (size_t)c->rows_cap_a * c->nd.PP, grid_b, c->nd.PP, n_out, c->d_gbuf, c->d_step, bump_step);
     c->step_launches++;
+    CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
+    return PINN_OK;
+}
+
+static void refresh_wq(pinn_ctx* c);
+
+// Fused reduce + peer-memory all-reduce + Adam (see reduce_exchange_adam_kernel).
+static int run_exchange_apply(pinn_ctx* c) {
+    P2PArgs x{};
+    for (int r = 0; r < c->cfg.nranks; r++) x.peers[r] = c->peer_ptr[r];
+    x.nranks = c->cfg.nranks; x.rank = c->cfg.rank; x.seq = ++c->xseq;
+    x.done_counter = c->d_done; x.err_flag = c->d_flag;
+    const int n_out = c->nd.P + 3;
+    reduce_exchange_adam_kernel<<<(n_out + 31) / 32, dim3(32, 32), 0, c->stream>>>(
+        c->nd, c->adam, c->d_partial, c->rows_a, c->d_partial + (size_t)c->rows_cap_a * c->nd.PP, c->rows_b,
+        c->d_params, c->d_paramsT, c->d_m, c->d_v, c->d_gbuf, c->d_step, (unsigned long long)(c->host_step + 1),
+        c->d_loss, c->d_flag, x);
+    c->step_launches++;
+    refresh_wq(c);
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
     return PINN_OK;
 }
@@ -578,7 +719,9 @@ static int run_apply(pinn_ctx* c, int apply) {
 
 // All device work of one training step, issued on the handle's streams (directly, or under capture).
 static int issue_step(pinn_ctx* c) {
-    int rc = run_local(c, 1);
+    const bool p2p = c->cfg.nranks > 1 && c->comm != nullptr && c->p2p_ready;
+    int rc = run_local(c, 1, !p2p);
+    if (p2p) return rc ? rc : run_exchange_apply(c);
     if (!rc) rc = run_allreduce(c);
     if (!rc) rc = run_apply(c, 1);
     return rc;
@@ -599,14 +742,15 @@ static int step_once(pinn_ctx* c) {
     const bool want_graph = c->graph_ok && !c->prof;
     const bool dist = c->cfg.nranks > 1 && c->comm != nullptr;
     if (want_graph) {
-        const uint64_t key[4] = {c->n_local[0], c->n_local[1], c->n_local[2], (uint64_t)dist};
+        const bool p2p = dist && c->p2p_ready;
+        const uint64_t key[4] = {c->n_local[0], c->n_local[1], c->n_local[2], (uint64_t)dist + 2 * (uint64_t)p2p};
         if (!c->graph_exec || memcmp(key, c->graph_key, sizeof(key)) != 0) {
             drop_graph(c);
             c->step_launches = 0; c->capturing = true;
             cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
             int rc = PINN_ERR_CUDA;
             if (e == cudaSuccess) {
-                rc = run_local(c, 1);
+                rc = run_local(c, 1, !p2p);               // with the peer exchange the reduction is part of the fused kernel
                 if (!rc && !dist) rc = run_apply(c, 1);
             }
             cudaGraph_t g = nullptr;
@@ -627,8 +771,9 @@ static int step_once(pinn_ctx* c) {
             c->launches += c->launches_per_graph;
             if (dist) {
                 c->step_launches = 0;
-                int rc = run_allreduce(c);
-                if (!rc) rc = run_apply(c, 1);
+                int rc;
+                if (p2p) rc = run_exchange_apply(c);
+                else { rc = run_allreduce(c); if (!rc) rc = run_apply(c, 1); }
                 c->launches += c->step_launches;
                 if (rc) return rc;
             }
@@ -772,6 +917,9 @@ void pinn_destroy(pinn_ctx* c) {
     cudaFree(c->d_params); cudaFree(c->d_paramsT); cudaFree(c->d_m); cudaFree(c->d_v);
     cudaFree(c->d_gbuf); cudaFree(c->d_partial); cudaFree(c->d_stash); cudaFree(c->d_loss);
     cudaFree(c->d_step); cudaFree(c->d_wq); cudaFree(c->d_ring);
+    for (int r = 0; r < kMaxP2PRanks; r++)
+        if (c->peer_ptr[r] && c->peer_ptr[r] != c->d_xchg) cudaIpcCloseMemHandle(c->peer_ptr[r]);
+    cudaFree(c->d_xchg); cudaFree(c->d_done);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     drop_graph(c);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -982,6 +1130,41 @@ int pinn_comm_init(pinn_ctx* c, const void* id128) {
     const int rc = g_nccl.CommInitRank(&c->comm, c->cfg.nranks, id, c->cfg.rank);
     if (rc != 0) return fail(c, PINN_ERR_NCCL, std::string("pinn_comm_init: ncclCommInitRank -> ") +
                                                    (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    return PINN_OK;
+}
+
+int pinn_comm_p2p_export(pinn_ctx* c, void* handle64) {
+    if (!c || !handle64) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_comm_p2p_export: null argument");
+    if (c->cfg.nranks > kMaxP2PRanks) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_comm_p2p_export: more than 16 ranks");
+    CUDA_TRY(c, "pinn_comm_p2p_export", cudaSetDevice(c->cfg.device));
+    if (!c->d_xchg) {
+        const size_t bytes = (kXchgHeader + 2 * (size_t)c->nd.PP) * sizeof(float);
+        CUDA_TRY(c, "pinn_comm_p2p_export", cudaMalloc(&c->d_xchg, bytes));
+        CUDA_TRY(c, "pinn_comm_p2p_export", cudaMemset(c->d_xchg, 0, bytes));
+        CUDA_TRY(c, "pinn_comm_p2p_export", cudaMalloc(&c->d_done, sizeof(unsigned int)));
+        CUDA_TRY(c, "pinn_comm_p2p_export", cudaMemset(c->d_done, 0, sizeof(unsigned int)));
+        CUDA_TRY(c, "pinn_comm_p2p_export", cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(c, "pinn_comm_p2p_export", cudaIpcGetMemHandle(&h, c->d_xchg));
+    static_assert(sizeof(h) == PINN_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, sizeof(h));
+    return PINN_OK;
+}
+
+int pinn_comm_p2p_open(pinn_ctx* c, const void* handles, int count) {
+    if (!c || !handles) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_comm_p2p_open: null argument");
+    if (count != c->cfg.nranks || !c->d_xchg) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_comm_p2p_open: need one handle per rank, after pinn_comm_p2p_export");
+    CUDA_TRY(c, "pinn_comm_p2p_open", cudaSetDevice(c->cfg.device));
+    for (int r = 0; r < count; r++) {
+        if (r == c->cfg.rank) { c->peer_ptr[r] = c->d_xchg; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + (size_t)r * PINN_IPC_HANDLE_BYTES, sizeof(h));
+        void* ptr = nullptr;
+        CUDA_TRY(c, "pinn_comm_p2p_open", cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_ptr[r] = static_cast<float*>(ptr);
+    }
+    c->p2p_ready = true;
     return PINN_OK;
 }
 

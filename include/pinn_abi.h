@@ -231,6 +231,16 @@ int pinn_synchronize(pinn_ctx* ctx);
 int pinn_comm_unique_id(void* id128);
 int pinn_comm_init(pinn_ctx* ctx, const void* id128);
 
+/* Optional fused collective (NVLink peer memory, one process per GPU on one box): every rank exports the
+ * IPC handle of its exchange buffer, the caller gathers the handles in rank order (64 bytes each) and
+ * every rank opens them.  From then on pinn_train_step replaces "reduce kernel + ncclAllReduce + Adam
+ * kernel" by ONE kernel per rank that sums its partial gradient rows, publishes the 4*(P+3)-byte sum,
+ * reads every peer's sum over NVLink in rank order (bit-identical result on all ranks) and applies
+ * Adam.  pinn_comm_init must have succeeded first (it validates the world). */
+#define PINN_IPC_HANDLE_BYTES 64
+int pinn_comm_p2p_export(pinn_ctx* ctx, void* handle64);
+int pinn_comm_p2p_open(pinn_ctx* ctx, const void* handles, int count);
+
 /* Alternative when the caller owns the collective (e.g. torch.distributed): split the step.
  * pinn_step_local computes local gradient/loss sums into the device buffer returned by
  * pinn_grad_buffer ([P+3] floats: gradients in parameter order, then sum r^2, sum bc^2,

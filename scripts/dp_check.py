@@ -23,6 +23,11 @@ net = P.Network(cfg)
 box = [P.Network.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(box, src=0)
 net.comm_init(box[0])
+p2p = os.environ.get("PINN_P2P", "1") != "0"
+if p2p:      # fused reduce + all-reduce + Adam over NVLink peer memory instead of NCCL
+    hs = [None] * world
+    dist.all_gather_object(hs, net.p2p_export())
+    net.p2p_open(hs)
 w0 = net.get_params()
 losses = [net.train_step()["loss"] for _ in range(K)]
 w = torch.from_numpy(net.get_params()).cuda()
@@ -45,7 +50,7 @@ if rank == 0:
     dl = float(np.abs(np.array(losses + [o["loss"]]) / l_ref[:, 0] - 1).max())
     dp = float(np.abs(net.get_params() - p_ref).max())
     good = ok and dl < 1e-5 and dp < 1e-5
-    print(f"DP_CHECK {'OK' if good else 'FAIL'} ranks={world} identical_across_ranks={ok} loss_rel={dl:.2e} params_abs={dp:.2e}", flush=True)
+    print(f"DP_CHECK {'OK' if good else 'FAIL'} ranks={world} collective={'p2p-fused' if p2p else 'nccl'} identical_across_ranks={ok} loss_rel={dl:.2e} params_abs={dp:.2e}", flush=True)
     if not good:
         sys.exit(1)
 net.close()
