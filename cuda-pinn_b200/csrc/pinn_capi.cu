@@ -122,20 +122,22 @@ __global__ void adam_kernel(const NetDims nd, const AdamArgs a, float* __restric
 
 // ------------------------------------------------------------------------------------------
 // Fused gradient reduction + all-reduce + Adam over NVLink peer memory (one kernel per rank per step).
-//   1. fixed-order sum of this GPU's CTA partial rows (as reduce_partials_kernel) into this rank's
-//      exchange buffer (IPC-mapped into every peer), parity = sequence number & 1;
-//   2. the last block to finish publishes the sequence number in the buffer's flag word
-//      (threadfence_system + release store);
-//   3. every block waits until every peer's flag has reached the sequence number (acquire loads over
-//      NVLink, bounded spin), then sums the R exchange buffers in RANK ORDER with cache-volatile peer
-//      loads — every rank adds the same numbers in the same order, so the weights stay bit-identical;
+// PUSH protocol — every rank owns an exchange buffer (IPC-mapped into all peers) with one slot per
+// SOURCE rank and parity, and one flag word per source rank:
+//   1. fixed-order sum of this GPU's CTA partial rows (as reduce_partials_kernel); each column sum is
+//      STORED into slot[this rank][parity] of EVERY rank's buffer (NVLink stores, fire and forget);
+//   2. the last block to finish does threadfence_system and release-stores the sequence number into
+//      flag[this rank] of every rank's buffer;
+//   3. every block polls only its OWN buffer's flags (local memory) until all sources have reached the
+//      sequence number (bounded spin), then sums the R local slots in RANK ORDER — every rank adds the
+//      same numbers in the same order, so the weights stay bit-identical;
 //   4. Adam on the summed gradient, loss record.
 // Replaces reduce kernel + ncclAllReduce + Adam kernel; the payload is P+3 floats (12 KB .. 1.8 MB).
-// Double buffering by parity + the flag protocol make a buffer reusable: a rank can only overwrite
-// parity q again after every peer has published the step in between, i.e. has finished reading q.
+// Parity double buffering + the flags make a slot reusable: a rank can write parity q of a peer again only
+// after that peer has published the step in between, i.e. after it finished reading q.
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxP2PRanks = 16;
-constexpr int kXchgHeader = 32;                         // floats reserved in front of the two payload slots
+constexpr int kXchgHeader = 32;                         // floats in front of the slots: one 64-bit flag per source rank
 struct P2PArgs {
     float* peers[kMaxP2PRanks];                          // exchange buffers in rank order (own included)
     int nranks, rank;
@@ -189,7 +191,8 @@ reduce_exchange_adam_kernel(const NetDims nd, const AdamArgs a, float* __restric
         float t = 0.0f;
         #pragma unroll
         for (int y = 0; y < 32; y++) t += part[y][threadIdx.x];
-        x.peers[x.rank][kXchgHeader + (size_t)par * PP + col] = t;      // this rank's local sum, visible to the peers
+        const size_t slot = kXchgHeader + ((size_t)(x.rank * 2 + par)) * PP + col;
+        for (int r = 0; r < x.nranks; r++) x.peers[r][slot] = t;        // push this rank's local sum to every rank (own included)
     }
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
@@ -198,23 +201,24 @@ reduce_exchange_adam_kernel(const NetDims nd, const AdamArgs a, float* __restric
         if (old == gridDim.x - 1) {                                    // every block of this rank has written its columns
             *x.done_counter = 0u;
             __threadfence_system();
-            st_release_sys(reinterpret_cast<unsigned long long*>(x.peers[x.rank]), x.seq);
+            for (int r = 0; r < x.nranks; r++)                         // announce: all my columns have landed in rank r's buffer
+                st_release_sys(reinterpret_cast<unsigned long long*>(x.peers[r]) + x.rank, x.seq);
             *step = tstep;
         }
         const long long t0 = clock64();
-        for (int r = 0; r < x.nranks; r++) {
-            if (r == x.rank) continue;
-            const unsigned long long* pf = reinterpret_cast<const unsigned long long*>(x.peers[r]);
-            while (ld_acquire_sys(pf) < x.seq) {
-                if (clock64() - t0 > 4000000000LL) { *x.err_flag = PINN_ERR_NCCL; break; }   // ~2 s: peer never arrived
-                __nanosleep(200);
+        const unsigned long long* my_flags = reinterpret_cast<const unsigned long long*>(x.peers[x.rank]);
+        for (int r = 0; r < x.nranks; r++) {                           // poll LOCAL memory only
+            while (ld_acquire_sys(my_flags + r) < x.seq) {
+                if (clock64() - t0 > 4000000000LL) { *x.err_flag = PINN_ERR_NCCL; break; }   // ~2 s: a peer never arrived
+                __nanosleep(100);
             }
         }
     }
     __syncthreads();
     if (threadIdx.y == 0 && col < n_out) {
+        const float* mine = x.peers[x.rank] + kXchgHeader;
         float g = 0.0f;
-        for (int r = 0; r < x.nranks; r++) g += __ldcv(x.peers[r] + kXchgHeader + (size_t)par * PP + col);   // rank order
+        for (int r = 0; r < x.nranks; r++) g += __ldcv(mine + ((size_t)(r * 2 + par)) * PP + col);   // rank order, local reads
         gbuf[col] = g;
         if (col < nd.P) {
             adam_one(nd, a, params, paramsT, m, v, g, (double)tstep, col);
@@ -223,7 +227,7 @@ reduce_exchange_adam_kernel(const NetDims nd, const AdamArgs a, float* __restric
             #pragma unroll
             for (int q = 0; q < 3; q++) {
                 float t = 0.0f;
-                for (int r = 0; r < x.nranks; r++) t += __ldcv(x.peers[r] + kXchgHeader + (size_t)par * PP + nd.P + q);
+                for (int r = 0; r < x.nranks; r++) t += __ldcv(mine + ((size_t)(r * 2 + par)) * PP + nd.P + q);
                 s3[q] = t;
             }
             loss_record(nd, a, s3[0], s3[1], s3[2], loss_out, flag);
@@ -1138,7 +1142,7 @@ int pinn_comm_p2p_export(pinn_ctx* c, void* handle64) {
     if (c->cfg.nranks > kMaxP2PRanks) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_comm_p2p_export: more than 16 ranks");
     CUDA_TRY(c, "pinn_comm_p2p_export", cudaSetDevice(c->cfg.device));
     if (!c->d_xchg) {
-        const size_t bytes = (kXchgHeader + 2 * (size_t)c->nd.PP) * sizeof(float);
+        const size_t bytes = (kXchgHeader + 2 * (size_t)c->cfg.nranks * (size_t)c->nd.PP) * sizeof(float);   // [source rank][parity][PP]
         CUDA_TRY(c, "pinn_comm_p2p_export", cudaMalloc(&c->d_xchg, bytes));
         CUDA_TRY(c, "pinn_comm_p2p_export", cudaMemset(c->d_xchg, 0, bytes));
         CUDA_TRY(c, "pinn_comm_p2p_export", cudaMalloc(&c->d_done, sizeof(unsigned int)));
