@@ -266,7 +266,7 @@ def main():
         dist.broadcast_object_list(box, src=0)
         net.comm_init(box[0])
         collective = "nccl all-reduce of [P+3] floats"
-        if os.environ.get("PINN_P2P", "1") != "0":
+        if os.environ.get("PINN_P2P", "0") == "1":
             hs = [None] * world
             dist.all_gather_object(hs, net.p2p_export())
             net.p2p_open(hs)

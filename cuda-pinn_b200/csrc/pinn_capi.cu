@@ -151,8 +151,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 __global__ void __launch_bounds__(1024)
@@ -196,13 +196,13 @@ reduce_exchange_adam_kernel(const NetDims nd, const AdamArgs a, float* __restric
     }
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-        __threadfence_system();
+        __threadfence();                                               // this block's pushes ordered before its arrival (GPU scope)
         const unsigned int old = atomicAdd(x.done_counter, 1u);
-        if (old == gridDim.x - 1) {                                    // every block of this rank has written its columns
+        if (old == gridDim.x - 1) {                                    // every block of this rank has pushed its columns
             *x.done_counter = 0u;
-            __threadfence_system();
-            for (int r = 0; r < x.nranks; r++)                         // announce: all my columns have landed in rank r's buffer
-                st_release_sys(reinterpret_cast<unsigned long long*>(x.peers[r]) + x.rank, x.seq);
+            __threadfence_system();                                    // ONE system fence (cumulative over the arrivals observed above) ...
+            for (int r = 0; r < x.nranks; r++)                         // ... then relaxed flag stores: all my columns have landed in rank r
+                st_relaxed_sys(reinterpret_cast<unsigned long long*>(x.peers[r]) + x.rank, x.seq);
             *step = tstep;
         }
         const long long t0 = clock64();

@@ -23,7 +23,7 @@ net = P.Network(cfg)
 box = [P.Network.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(box, src=0)
 net.comm_init(box[0])
-p2p = os.environ.get("PINN_P2P", "1") != "0"
+p2p = os.environ.get("PINN_P2P", "0") == "1"
 if p2p:      # fused reduce + all-reduce + Adam over NVLink peer memory instead of NCCL
     hs = [None] * world
     dist.all_gather_object(hs, net.p2p_export())
