@@ -42,6 +42,10 @@ class PinnStepOut(C.Structure):
                 ("mse_initial", C.c_float), ("step", C.c_uint64)]
 
 
+class PinnEvalOut(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("rel_l2", C.c_double * 3), ("max_abs", C.c_double * 3), ("mse_residual", C.c_double)]
+
+
 class PinnProfile(C.Structure):
     _fields_ = [("launches", C.c_uint64), ("step_kernel_ms", C.c_double), ("step_kernel_count", C.c_uint64),
                 ("grid", C.c_int32), ("block", C.c_int32), ("smem_bytes", C.c_int32), ("kernel_id", C.c_int32)]
@@ -55,6 +59,7 @@ ABI_SYMBOLS = [
     "pinn_sample_points", "pinn_resample_points", "pinn_set_points", "pinn_get_points", "pinn_local_count",
     "pinn_train_step", "pinn_train_step_host", "pinn_train_steps", "pinn_loss_grad",
     "pinn_forward", "pinn_residual", "pinn_synchronize",
+    "pinn_save", "pinn_load", "pinn_exact_solution", "pinn_evaluate",
     "pinn_comm_unique_id", "pinn_comm_init", "pinn_comm_p2p_export", "pinn_comm_p2p_open", "pinn_step_local", "pinn_step_apply",
     "pinn_grad_buffer", "pinn_stream", "pinn_profile_enable", "pinn_profile_get",
 ]
@@ -104,6 +109,10 @@ def lib():
     L.pinn_forward.argtypes = [vp, vp, vp, C.c_size_t]
     L.pinn_residual.argtypes = [vp, vp, vp, vp, C.c_size_t]
     L.pinn_synchronize.argtypes = [vp]
+    L.pinn_save.argtypes = [vp, C.c_char_p]
+    L.pinn_load.argtypes = [vp, C.c_char_p]
+    L.pinn_exact_solution.argtypes = [cfgp, vp, vp, C.c_size_t]
+    L.pinn_evaluate.argtypes = [vp, C.c_int, P(PinnEvalOut)]
     L.pinn_comm_unique_id.argtypes = [vp]
     L.pinn_comm_init.argtypes = [vp, vp]
     L.pinn_comm_p2p_export.argtypes = [vp, vp]
@@ -137,6 +146,16 @@ def shard_range(n, rank, nranks):
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def exact_solution(cfg, x):
+    """Analytic solution u*(x) [n, d_out] where the PDE has one (pinn_exact_solution); PinnError(7) otherwise."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    u = np.empty((len(x), cfg.d_out), dtype=np.float32)
+    rc = lib().pinn_exact_solution(C.byref(cfg), _ptr(x), _ptr(u), len(x))
+    if rc:
+        raise PinnError(rc, "pinn_exact_solution: no analytic solution for this pde" if rc == 7 else "pinn_exact_solution: invalid argument")
+    return u
 
 
 class Network:
@@ -272,6 +291,20 @@ class Network:
 
     def synchronize(self):
         self._check(self._L.pinn_synchronize(self._h))
+
+    # -- checkpoint + evaluation
+    def save(self, path):
+        self._check(self._L.pinn_save(self._h, os.fsencode(path)))
+
+    def load(self, path):
+        self._check(self._L.pinn_load(self._h, os.fsencode(path)))
+
+    def evaluate(self, per_axis):
+        """Grid evaluation: relative L2 / max error vs the analytic solution (NaN if none) and residual MSE."""
+        o = PinnEvalOut()
+        self._check(self._L.pinn_evaluate(self._h, per_axis, C.byref(o)))
+        k = self.cfg.d_out
+        return dict(n=int(o.n), rel_l2=list(o.rel_l2)[:k], max_abs=list(o.max_abs)[:k], mse_residual=o.mse_residual)
 
     # -- multi-GPU
     @staticmethod

@@ -1,11 +1,14 @@
 // pinn_capi.cu — host side of the B200 PINN train step behind the C ABI of include/pinn_abi.h.
 // Owns device memory, the stream, kernel selection and (N>1) the NCCL communicator.
-// There is no CPU arithmetic path here: every entry point either runs CUDA kernels or fails.
+// There is no CPU arithmetic path for the step: every compute entry point runs CUDA kernels or fails
+// (host arithmetic exists only for the analytic comparison solutions of pinn_exact_solution).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <algorithm>
+#include <memory>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -1108,6 +1111,135 @@ static int eval_common(pinn_ctx* c, const char* fn, bool full, const float* x, f
 
 int pinn_forward(pinn_ctx* c, const float* x, float* y, size_t n) { return eval_common(c, "pinn_forward", false, x, y, nullptr, n); }
 int pinn_residual(pinn_ctx* c, const float* x, float* y, float* r, size_t n) { return eval_common(c, "pinn_residual", true, x, y, r, n); }
+
+// ---- checkpoint + evaluation ----------------------------------------------------
+namespace {
+struct CkptHeader {                     // 64 bytes, little-endian (pinn_abi.h: pinn_save)
+    char     magic[8];
+    uint32_t version;
+    int32_t  pde, d_in, d_out, width, depth;
+    uint32_t reserved0[2];
+    uint64_t P, step;
+    uint8_t  reserved1[8];
+};
+static_assert(sizeof(CkptHeader) == 64, "checkpoint header is 64 bytes");
+const char kCkptMagic[8] = {'P', 'I', 'N', 'N', 'C', 'K', 'P', 'T'};
+struct FileCloser { void operator()(FILE* f) const { if (f) fclose(f); } };
+}  // namespace
+
+int pinn_save(pinn_ctx* c, const char* path) {
+    if (!c || !path) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_save: null argument");
+    const size_t P = (size_t)c->nd.P;
+    std::vector<float> w(P), m(P), v(P);
+    uint64_t step = 0;
+    int rc = pinn_get_params(c, w.data(), P);
+    if (rc) return rc;
+    rc = pinn_get_optimizer(c, m.data(), v.data(), P, &step);
+    if (rc) return rc;
+    CkptHeader h{};
+    memcpy(h.magic, kCkptMagic, 8);
+    h.version = 1; h.pde = c->cfg.pde; h.d_in = c->cfg.d_in; h.d_out = c->cfg.d_out; h.width = c->cfg.width; h.depth = c->cfg.depth;
+    h.P = P; h.step = step;
+    std::unique_ptr<FILE, FileCloser> f(fopen(path, "wb"));
+    if (!f) return fail(c, PINN_ERR_INVALID_ARGUMENT, std::string("pinn_save: cannot open ") + path);
+    const bool ok = fwrite(&h, sizeof(h), 1, f.get()) == 1 && fwrite(w.data(), sizeof(float), P, f.get()) == P &&
+                    fwrite(m.data(), sizeof(float), P, f.get()) == P && fwrite(v.data(), sizeof(float), P, f.get()) == P &&
+                    fflush(f.get()) == 0;
+    if (!ok) return fail(c, PINN_ERR_INVALID_ARGUMENT, std::string("pinn_save: short write to ") + path);
+    return PINN_OK;
+}
+
+int pinn_load(pinn_ctx* c, const char* path) {
+    if (!c || !path) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_load: null argument");
+    std::unique_ptr<FILE, FileCloser> f(fopen(path, "rb"));
+    if (!f) return fail(c, PINN_ERR_INVALID_ARGUMENT, std::string("pinn_load: cannot open ") + path);
+    CkptHeader h{};
+    if (fread(&h, sizeof(h), 1, f.get()) != 1 || memcmp(h.magic, kCkptMagic, 8) != 0)
+        return fail(c, PINN_ERR_INVALID_ARGUMENT, std::string("pinn_load: not a checkpoint - ") + path);
+    if (h.version != 1) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_load: unknown checkpoint version " + std::to_string(h.version));
+    if (h.pde != c->cfg.pde || h.d_in != c->cfg.d_in || h.d_out != c->cfg.d_out || h.width != c->cfg.width ||
+        h.depth != c->cfg.depth || h.P != (uint64_t)c->nd.P)
+        return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_load: network mismatch - file has pde " + std::to_string(h.pde) + " " +
+                    std::to_string(h.d_in) + "->[" + std::to_string(h.width) + "x" + std::to_string(h.depth) + "]->" + std::to_string(h.d_out));
+    const size_t P = (size_t)h.P;
+    std::vector<float> w(P), m(P), v(P);
+    if (fread(w.data(), sizeof(float), P, f.get()) != P || fread(m.data(), sizeof(float), P, f.get()) != P ||
+        fread(v.data(), sizeof(float), P, f.get()) != P)
+        return fail(c, PINN_ERR_INVALID_ARGUMENT, std::string("pinn_load: truncated checkpoint - ") + path);
+    int rc = pinn_set_params(c, w.data(), P, 0);
+    if (rc) return rc;
+    return pinn_set_optimizer(c, m.data(), v.data(), P, h.step);
+}
+
+int pinn_exact_solution(const pinn_config* cfg, const float* x, float* u, size_t n) {
+    if (!cfg || (n && (!x || !u))) return PINN_ERR_INVALID_ARGUMENT;
+    int n_space, n2, n_res, d_out;
+    if (!pde_shape(cfg->pde, &n_space, &n2, &n_res, &d_out)) return PINN_ERR_INVALID_ARGUMENT;
+    const double pi = 3.14159265358979323846;
+    const int d = cfg->d_in;
+    switch (cfg->pde) {
+    case PINN_PDE_HELMHOLTZ:
+        for (size_t i = 0; i < n; i++) u[i] = (float)(sin(pi * x[i * d]) * sin(4.0 * pi * x[i * d + 1]));
+        return PINN_OK;
+    case PINN_PDE_HEAT:
+        for (size_t i = 0; i < n; i++)
+            u[i] = (float)(sin(pi * x[i * d]) * sin(pi * x[i * d + 1]) * exp(-2.0 * (double)kHeatAlpha * pi * pi * x[i * d + 2]));
+        return PINN_OK;
+    case PINN_PDE_NAVIER_STOKES:
+        for (size_t i = 0; i < n; i++) {
+            const double X = x[i * d], Y = x[i * d + 1], T = x[i * d + 2];
+            const double e2 = exp(-2.0 * (double)kNsNu * T), e4 = exp(-4.0 * (double)kNsNu * T);
+            u[i * 3 + 0] = (float)(-cos(X) * sin(Y) * e2);
+            u[i * 3 + 1] = (float)(sin(X) * cos(Y) * e2);
+            u[i * 3 + 2] = (float)(-0.25 * (cos(2.0 * X) + cos(2.0 * Y)) * e4);
+        }
+        return PINN_OK;
+    default:
+        return PINN_ERR_UNSUPPORTED;     // Burgers, Allen-Cahn: no closed form
+    }
+}
+
+int pinn_evaluate(pinn_ctx* c, int per_axis, pinn_eval_out* out) {
+    if (!c || !out) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_evaluate: null argument");
+    if (per_axis < 2 || per_axis > 4096) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_evaluate: per_axis must be in [2, 4096]");
+    const NetDims& nd = c->nd;
+    const int d = nd.d_in, C = nd.C, O = nd.d_out, R = nd.n_res;
+    uint64_t total = 1;
+    for (int k = 0; k < d; k++) total *= (uint64_t)per_axis;
+    if (total > ((uint64_t)1 << 32)) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_evaluate: grid larger than 2^32 nodes");
+    memset(out, 0, sizeof(*out));
+    out->n = total;
+    const size_t chunk = 1 << 18;
+    std::vector<float> x(chunk * d), y(chunk * O * C), r(chunk * R), u(chunk * O);
+    double num[3] = {0, 0, 0}, den[3] = {0, 0, 0}, mx[3] = {0, 0, 0}, rs = 0.0;
+    bool exact = true;
+    for (uint64_t i0 = 0; i0 < total; i0 += chunk) {
+        const size_t m = (size_t)std::min<uint64_t>(chunk, total - i0);
+        for (size_t i = 0; i < m; i++) {
+            uint64_t q = i0 + i;
+            for (int k = d; k-- > 0;) {
+                const uint64_t idx = q % (uint64_t)per_axis; q /= (uint64_t)per_axis;
+                x[i * d + k] = nd.lo[k] + nd.span[k] * (float)idx / (float)(per_axis - 1);
+            }
+        }
+        int rc = eval_common(c, "pinn_evaluate", true, x.data(), y.data(), r.data(), m);
+        if (rc) return rc;
+        for (size_t i = 0; i < m * (size_t)R; i++) rs += (double)r[i] * (double)r[i];
+        if (exact && pinn_exact_solution(&c->cfg, x.data(), u.data(), m) != PINN_OK) exact = false;
+        if (exact)
+            for (size_t i = 0; i < m; i++)
+                for (int o = 0; o < O; o++) {
+                    const double t = u[i * O + o], e = (double)y[(i * O + o) * C] - t;
+                    num[o] += e * e; den[o] += t * t; mx[o] = std::max(mx[o], fabs(e));
+                }
+    }
+    out->mse_residual = rs / (double)total;
+    for (int o = 0; o < 3; o++) {
+        out->rel_l2[o] = (exact && o < O) ? sqrt(num[o] / (den[o] > 0.0 ? den[o] : 1.0)) : NAN;
+        out->max_abs[o] = (exact && o < O) ? mx[o] : NAN;
+    }
+    return PINN_OK;
+}
 
 int pinn_synchronize(pinn_ctx* c) {
     if (!c) return PINN_ERR_INVALID_ARGUMENT;

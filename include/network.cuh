@@ -264,4 +264,35 @@ class network {
             this->check(pinn_residual(this->ctx, x.raw(), &y[0], nullptr, n), "derivatives");
             return y;
         }
+
+        // ---- checkpoint + evaluation ----
+        // Flat binary file: header, parameters, Adam moments, step counter; load resumes bit-exactly.
+        const network &save(const std::string &path) const {
+            this->check(pinn_save(this->ctx, path.c_str()), "save");
+            return *this;
+        }
+
+        network &load(const std::string &path) {
+            this->check(pinn_load(this->ctx, path.c_str()), "load");
+            this->device_dirty = true;
+            return *this;
+        }
+
+        // Analytic solution u*[n, d_out] at caller points; throws std::runtime_error where the PDE has none.
+        [[nodiscard]] tensor<T> exact(const tensor<T> &x) const {
+            if (x.dim() != 2 || x.get_shape()[1] != static_cast<size_t>(this->cfg.d_in))
+                throw std::invalid_argument{"network::exact: expected a [n, d_in] matrix"};
+            const size_t n = x.get_shape()[0];
+            tensor<T> u(as_shape, {n, static_cast<size_t>(this->cfg.d_out)});
+            if (pinn_exact_solution(&this->cfg, x.raw(), &u[0], n) != PINN_OK)
+                throw std::runtime_error{"network::exact: this pde has no analytic solution"};
+            return u;
+        }
+
+        // Error norms against the analytic solution on a regular grid (per_axis nodes per input axis).
+        [[nodiscard]] pinn_eval_out evaluate(size_t per_axis) const {
+            pinn_eval_out o{};
+            this->check(pinn_evaluate(this->ctx, static_cast<int>(per_axis), &o), "evaluate");
+            return o;
+        }
 };

@@ -252,6 +252,38 @@ void* pinn_grad_buffer(pinn_ctx* ctx, size_t* n_floats);   /* DEVICE pointer */
 void* pinn_stream(pinn_ctx* ctx);                           /* cudaStream_t */
 
 /* ---------------------------------------------------------------------------------------- */
+/* checkpoint + evaluation (the reference has neither)                    */
+/* ---------------------------------------------------------------------------------------- */
+
+/* Flat little-endian binary checkpoint: 64-byte header {"PINNCKPT", u32 version = 1, i32 pde, d_in,
+ * d_out, width, depth, u32 reserved[2], u64 P, u64 step, 8 reserved bytes} followed by params[P], m[P],
+ * v[P] as float32.  What tensor<T>::raw() + fwrite of every W/b would be in the reference
+ * (init_tensor.h:303), as one file.  pinn_load checks the header against the handle's network
+ * (PINN_ERR_INVALID_ARGUMENT on any mismatch, the handle is left untouched) and restores parameters,
+ * Adam moments and the step counter: a resumed run continues bit-exactly. */
+int pinn_save(pinn_ctx* ctx, const char* path);
+int pinn_load(pinn_ctx* ctx, const char* path);
+
+/* Analytic solution u*(x) of the PDE where Appendix B has one (HOST buffers, host arithmetic in double,
+ * x is [n, d_in], u is [n, d_out]): Helmholtz sin(pi x) sin(4 pi y); heat sin(pi x) sin(pi y)
+ * exp(-2 alpha pi^2 t); Navier-Stokes Taylor-Green (u, v, p).  Burgers and Allen-Cahn have no closed
+ * form here: PINN_ERR_UNSUPPORTED. */
+int pinn_exact_solution(const pinn_config* cfg, const float* x, float* u, size_t n);
+
+typedef struct pinn_eval_out {
+    uint64_t n;              /* grid nodes evaluated (per_axis ^ d_in) */
+    double   rel_l2[3];      /* per output: ||y - u*||_2 / ||u*||_2 over the grid */
+    double   max_abs[3];     /* per output: max |y - u*| */
+    double   mse_residual;   /* mean over the grid of sum_k r_k^2 (PDE residual of the network) */
+} pinn_eval_out;
+
+/* Evaluate the network on the regular grid of per_axis nodes per input axis over the PDE's box
+ * (row-major, last axis fastest, end points included): forward + residual on the device (the same
+ * kernels as pinn_residual), error norms against pinn_exact_solution accumulated in double on the
+ * host.  For PDEs without an analytic solution rel_l2/max_abs are NaN and only mse_residual is set. */
+int pinn_evaluate(pinn_ctx* ctx, int per_axis, pinn_eval_out* out);
+
+/* ---------------------------------------------------------------------------------------- */
 /* measurement hooks (bench.py)                                                             */
 /* ---------------------------------------------------------------------------------------- */
 

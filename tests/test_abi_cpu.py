@@ -96,3 +96,44 @@ def test_product_sources_never_touch_the_oracle():
                     if re.search(r"import\s+oracle|from\s+oracle|liboracle|oracle/|oracle\.|include.*oracle|dlopen.*oracle", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_exact_solutions_match_closed_forms_and_oracle_targets(P, oracle):
+    """pinn_exact_solution is host arithmetic: checked here against numpy closed forms and, for Navier-Stokes
+    (whose Dirichlet/initial target IS the Taylor-Green solution), against the oracle's target function."""
+    rng = np.random.default_rng(7)
+    x2 = rng.uniform(-1, 1, (257, 2)).astype(np.float32)
+    x3 = np.concatenate([rng.uniform(-1, 1, (257, 2)), rng.uniform(0, 1, (257, 1))], axis=1).astype(np.float32)
+    xn = np.concatenate([rng.uniform(0, 2 * np.pi, (257, 2)), rng.uniform(0, 1, (257, 1))], axis=1).astype(np.float32)
+    d = x2.astype(np.float64)
+    u = P.exact_solution(P.default_config(3), x2)
+    assert np.allclose(u[:, 0], np.sin(np.pi * d[:, 0]) * np.sin(4 * np.pi * d[:, 1]), atol=1e-6)
+    heat = P.default_config(4, pde=P.PDE_HEAT)
+    d = x3.astype(np.float64)
+    u = P.exact_solution(heat, x3)
+    assert np.allclose(u[:, 0], np.sin(np.pi * d[:, 0]) * np.sin(np.pi * d[:, 1]) * np.exp(-2 * 0.05 * np.pi ** 2 * d[:, 2]), atol=1e-6)
+    u = P.exact_solution(P.default_config(5), xn)
+    assert u.shape == (257, 3)
+    assert np.allclose(u, oracle.target(oracle.baseline_config(5), 1, xn), atol=2e-6)
+    # initial target of the heat problem is the exact solution at t = 0
+    x0 = x3.copy(); x0[:, 2] = 0
+    ocfg_heat = oracle.make_config(oracle.PDE_HEAT, 16, 2, 64, 64, 64)
+    assert np.allclose(P.exact_solution(heat, x0), oracle.target(ocfg_heat, 2, x0), atol=2e-6)
+    for which in (1, 4):                       # Burgers, Allen-Cahn: no closed form
+        with pytest.raises(P.PinnError) as e:
+            P.exact_solution(P.default_config(which), x3[:, :P.default_config(which).d_in])
+        assert e.value.code == 7
+    assert P.exact_solution(P.default_config(3), np.zeros((0, 2), np.float32)).shape == (0, 1)
+
+
+def test_training_driver_argument_errors_without_a_gpu():
+    exe = os.path.join(ROOT, "bin", "pinn_train")
+    if not os.path.exists(exe):
+        pytest.skip("bin/pinn_train is built only where the reference headers are present")
+    import subprocess
+    r = subprocess.run([exe, "--bogus", "1"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "unknown option --bogus" in r.stderr
+    import torch
+    if not torch.cuda.is_available():          # no CPU fallback: the driver reports the library's error and exits 1
+        r = subprocess.run([exe, "--config", "1", "--steps", "1"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 1 and "pinn_train: " in r.stderr
