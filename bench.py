@@ -55,6 +55,23 @@ def traffic_for(which, prec_name):
         return None
 
 
+def mma_sync_line(prec_name, points, k_ms, depth):
+    """Issued tensor work of the width-20 mma.sync kernel against the measured mma.sync BF16 peak (profiles/mma_sync_peak.json)."""
+    pairs = 6 if prec_name == "bf16x6" else 3
+    # per 16-point warp tile and hidden->hidden layer: forward and dA = C x 3 n-tiles x pairs x (m16n8k16 + m16n8k8),
+    # dW = C x 3 n-tiles x pairs x 2 m-tiles x m16n8k16
+    per_tile_layer = 4 * 3 * pairs * (2 * (4096 + 2048) + 2 * 4096)
+    issued = points / 16.0 * (depth - 1) * per_tile_layer
+    peak = 549.8
+    try:
+        with open(os.path.join(ROOT, "profiles", "mma_sync_peak.json")) as f:
+            peak = float(json.load(f)["bf16_m16n8k16_tflops"])
+    except Exception:
+        pass
+    tf = issued / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    return {"issued_tflops": tf, "peak": peak, "frac": tf / peak, "of": "measured mma.sync m16n8k16 BF16 peak, tests/cuda/mma_sync_peak.cu"}
+
+
 def traffic_bytes(which, prec_name, points):
     t = traffic_for(which, prec_name)
     return None if not t else t["bytes_per_point"] * points
@@ -219,7 +236,7 @@ def main():
     ap.add_argument("--points", type=int, default=0, help="interior points per GPU (default: the config's)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("PINN_BENCH_PRECISION", "auto"),
-                    choices=["auto", "fp32", "bf16x3", "bf16"],
+                    choices=["auto", "fp32", "bf16x3", "bf16", "bf16x6"],
                     help="contraction arithmetic: fp32 CUDA cores | bf16x3 / bf16 tcgen05 (width 64/128/256); "
                          "auto = fp32 for width < 64, bf16x3 for 64/128, bf16 for 256")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -256,8 +273,9 @@ def main():
     width = {1: 20, 2: 20, 3: 64, 4: 128, 5: 256}[which]
     prec_name = args.precision
     if prec_name == "auto":
-        prec_name = "fp32" if width < 64 else ("bf16x3" if width <= 128 else "bf16")
-    prec = {"fp32": P.PREC_FP32, "bf16x3": P.PREC_BF16X3, "bf16": P.PREC_BF16}[prec_name]
+        # width 20 Burgers (C1, C2): FP32-equivalent 3-term split on mma.sync; other narrow nets: FP32 CUDA cores
+        prec_name = ("bf16x6" if which in (1, 2) and width == 20 else "fp32") if width < 64 else ("bf16x3" if width <= 128 else "bf16")
+    prec = {"fp32": P.PREC_FP32, "bf16x3": P.PREC_BF16X3, "bf16": P.PREC_BF16, "bf16x6": P.PREC_BF16X6}[prec_name]
     cfg = P.default_config(which, n_interior=nf, n_boundary=nb, n_initial=n0, rank=rank, nranks=world,
                            device=local_rank, precision=prec)
     net = P.Network(cfg)
@@ -342,9 +360,17 @@ def main():
         n_loc0 = net.local_count(0)
         ach_tf = n_loc0 * flops_pt / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
         ach_gb = n_loc0 * bytes_pt / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-        tensor_path = prec_name != "fp32"
+        narrow_mma = prof["kernel_id"] in (202, 203)      # register-chained mma.sync kernel (width 20)
+        tensor_path = prec_name != "fp32" and not narrow_mma
         mma_mult = 3 if prec_name == "bf16x3" else 1     # issued tensor FLOPs per algorithmic FLOP
-        if tensor_path:
+        if narrow_mma:
+            # FP32-equivalent throughput against the FP32 FMA peak (the pipe this kernel replaces, same denominator as the
+            # FP32 kernel's line); the issued tensor work against the measured mma.sync peak is reported beside it
+            rf_bound = "fp32_fma"
+            rf_peak, rf_src = fp32_peak()
+            rf_src += "; FP32-equivalent algorithmic FLOPs 6CW/pt executed as split-BF16 mma.sync products"
+            rf_kernel = f"fused_step_mma (interior, mma.sync {prec_name}, activations chained in registers)"
+        elif tensor_path:
             rf_bound, rf_peak = "tensor", pk["bf16_tflops_sustained"]
             rf_src = f"{pk['source']} bf16_tflops_sustained (MEASURED_PEAKS.json); algorithmic FLOPs 6CW/pt, issued tensor FLOPs x{mma_mult}"
             rf_kernel = "fused_step_tc (interior, tcgen05 " + prec_name + ")"
@@ -356,6 +382,7 @@ def main():
             "bound": rf_bound, "kernel": rf_kernel, "achieved": ach_tf, "peak": rf_peak,
             "unit": "TFLOP/s", "frac": ach_tf / rf_peak, "traffic": traffic_bytes(which, prec_name, n_loc0), "traffic_source": (traffic_for(which, prec_name) or {}).get("source"),
             "peak_source": rf_src, "issued_tensor_tflops": ach_tf * mma_mult if tensor_path else 0.0,
+            "mma_sync": mma_sync_line(prec_name, n_loc0, k_ms, cfg.depth) if narrow_mma else None,
             "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step if ms_step else None,
             "hbm": {"achieved": ach_gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_gb / pk["hbm_gbs"], "of": pk["source"]},
             "tensor": {"achieved": ach_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -366,7 +393,9 @@ def main():
             "metric": "collocation points/sec per train step (fwd+residual+bwd+Adam)",
             "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 operands (2-term split), f32 accumulate + f32 elementwise",
+            "dtype": {"fp32": "f32", "bf16x6": "f32-equivalent: operands split into 3 bf16 terms (exact 24-bit split), 6 mma.sync products, "
+                                               "f32 accumulate + f32 elementwise",
+                      "bf16x3": "bf16x3 operands (2-term split), f32 accumulate + f32 elementwise",
                       "bf16": "bf16 operands, f32 accumulate + f32 elementwise"}[prec_name], "data": "synthetic",
             "config": {"workload": CONFIG_NAMES[which], "precision": prec_name, "points_per_gpu": per_gpu, "n_interior": nf, "n_boundary": nb,
                        "n_initial": n0, "parallelism": f"dp{world}", "collective": collective if world > 1 else None, "l2": "flushed (256 MiB memset) between timed steps",

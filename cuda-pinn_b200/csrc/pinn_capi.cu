@@ -18,6 +18,7 @@
 #include "pinn_fused_fp32.cuh"
 #include "pinn_fused_tc.cuh"
 #include "pinn_fused_warp.cuh"
+#include "pinn_fused_mma.cuh"
 
 using namespace pinn;
 
@@ -40,7 +41,7 @@ __global__ void sample_points_kernel(const NetDims nd, int set, uint64_t seed, u
 // adds rows y, y+32, ... of range A then of range B; the 32 lane sums are combined in lane order.
 __global__ void __launch_bounds__(1024)
 reduce_partials_kernel(float* __restrict__ part_a, int rows_a, float* __restrict__ part_b, int rows_b, int PP, int n_out,
-                       float* __restrict__ gbuf, unsigned long long* step, int bump) {
+                       float* __restrict__ gbuf, unsigned long long* step, int bump, int zero_a) {
     __shared__ float part[32][33];
     constexpr int RU = 8;                                // independent loads in flight per thread
     const int col = blockIdx.x * 32 + threadIdx.x;
@@ -61,7 +62,7 @@ reduce_partials_kernel(float* __restrict__ part_a, int rows_a, float* __restrict
         };
         sum_rows(part_a, rows_a);
         sum_rows(part_b, rows_b);
-        for (int r = threadIdx.y; r < rows_a; r += 32) part_a[(size_t)r * PP + col] = 0.0f;
+        if (zero_a) for (int r = threadIdx.y; r < rows_a; r += 32) part_a[(size_t)r * PP + col] = 0.0f;   // (store-first rows need none)
         for (int r = threadIdx.y; r < rows_b; r += 32) part_b[(size_t)r * PP + col] = 0.0f;
     }
     part[threadIdx.y][threadIdx.x] = s;
@@ -80,10 +81,32 @@ struct AdamArgs {
     double inv_nf, inv_nb, inv_n0;
 };
 
-// Adam for parameter i + refresh of the transposed mirror W^T[l] ([fan_out, fan_in]).
+// Fragment-ordered BF16 mirror of the width-20 mma.sync kernel (pinn_fused_mma.cuh, layout of pack_wfrag_kernel),
+// viewed as 16-bit halves; w16 == nullptr: the handle has none.
+struct FragMirror { unsigned short* w16; int nterms; };
+
+// the BF16 terms of hidden->hidden weight W_l[k][j] into both directions of the mirror
+__device__ __forceinline__ void frag_mirror_store(const FragMirror& fm, int l, int k, int j, float w) {
+    uint32_t f[3];
+    split_pair<3>(w, 0.0f, f);                              // low halves: hi, mid, lo of w
+    const int words = 9 * fm.nterms;
+    #pragma unroll
+    for (int dir = 0; dir < 2; dir++) {
+        const int kk = dir ? j : k, n = dir ? k : j;        // dir 0: B[k][n] = W[k][n];  dir 1: B[k][n] = W[n][k]
+        const int r = kk < 8 ? 0 : (kk < 16 ? 1 : 2), kl = kk - 8 * r;
+        const int lane = (n & 7) * 4 + (kl >> 1);
+        for (int term = 0; term < fm.nterms; term++) {
+            const size_t word = ((size_t)((l - 2) * 2 + dir) * words + ((n >> 3) * fm.nterms + term) * 3 + r) * 32 + lane;
+            fm.w16[word * 2 + (kl & 1)] = (unsigned short)(f[term] & 0xffffu);
+        }
+    }
+}
+
+// Adam for parameter i + refresh of the transposed mirror W^T[l] ([fan_out, fan_in]) and, where the
+// handle has one, of the BF16 fragment mirror.
 __device__ __forceinline__ void adam_one(const NetDims& nd, const AdamArgs& a, float* __restrict__ params,
                                          float* __restrict__ paramsT, float* __restrict__ m, float* __restrict__ v,
-                                         float g, double t, int i) {
+                                         float g, double t, int i, const FragMirror& fm) {
     const float c1 = (float)(1.0 / (1.0 - pow((double)a.beta1, t)));
     const float c2 = (float)(1.0 / (1.0 - pow((double)a.beta2, t)));
     const float mi = a.beta1 * m[i] + (1.0f - a.beta1) * g;
@@ -98,6 +121,7 @@ __device__ __forceinline__ void adam_one(const NetDims& nd, const AdamArgs& a, f
     if (i < nd.offB[l]) {
         const int r = i - nd.offW[l], k = r / fo, j = r - k * fo;
         paramsT[nd.offW[l] + j * fi + k] = w;
+        if (fm.w16 && l >= 2 && l <= nd.L) frag_mirror_store(fm, l, k, j, w);
     } else {
         paramsT[i] = w;
     }
@@ -116,11 +140,63 @@ __device__ __forceinline__ void loss_record(const NetDims& nd, const AdamArgs& a
 __global__ void adam_kernel(const NetDims nd, const AdamArgs a, float* __restrict__ params,
                             float* __restrict__ paramsT, float* __restrict__ m, float* __restrict__ v,
                             const float* __restrict__ gbuf, const unsigned long long* __restrict__ step,
-                            float* __restrict__ loss_out, int* __restrict__ flag, int apply) {
+                            float* __restrict__ loss_out, int* __restrict__ flag, int apply, const FragMirror fm) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) loss_record(nd, a, gbuf[nd.P + 0], gbuf[nd.P + 1], gbuf[nd.P + 2], loss_out, flag);
     if (i >= nd.P || !apply) return;
-    adam_one(nd, a, params, paramsT, m, v, gbuf[i], (double)(*step), i);
+    adam_one(nd, a, params, paramsT, m, v, gbuf[i], (double)(*step), i, fm);
+}
+
+// Single-GPU step tail in ONE launch: fixed-order sum of the partial rows (as reduce_partials_kernel), Adam on the
+// block's own 32 columns, mirrors; the last block to finish records the loss and bumps the step counter.
+__global__ void __launch_bounds__(1024)
+reduce_adam_kernel(const NetDims nd, const AdamArgs a, float* __restrict__ part_a, int rows_a, int zero_a,
+                   float* __restrict__ part_b, int rows_b, float* __restrict__ params, float* __restrict__ paramsT,
+                   float* __restrict__ m, float* __restrict__ v, float* __restrict__ gbuf, unsigned long long* __restrict__ step,
+                   float* __restrict__ loss_out, int* __restrict__ flag, unsigned int* __restrict__ done_counter, const FragMirror fm) {
+    __shared__ float part[32][33];
+    constexpr int RU = 8;
+    const int PP = nd.PP, n_out = nd.P + 3;
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    const unsigned long long tstep = *step + 1ULL;         // every block reads it before the LAST block writes it back
+    float s = 0.0f;
+    if (col < n_out) {
+        auto sum_rows = [&](const float* __restrict__ base, int rows) {
+            for (int r0 = threadIdx.y; r0 < rows; r0 += 32 * RU) {
+                float vv[RU];
+                #pragma unroll
+                for (int u = 0; u < RU; u++) {
+                    const int r = r0 + 32 * u;
+                    vv[u] = (r < rows) ? __ldcg(base + (size_t)r * PP + col) : 0.0f;
+                }
+                #pragma unroll
+                for (int u = 0; u < RU; u++) s += vv[u];
+            }
+        };
+        sum_rows(part_a, rows_a);
+        sum_rows(part_b, rows_b);
+        if (zero_a) for (int r = threadIdx.y; r < rows_a; r += 32) part_a[(size_t)r * PP + col] = 0.0f;
+        for (int r = threadIdx.y; r < rows_b; r += 32) part_b[(size_t)r * PP + col] = 0.0f;
+    }
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < n_out) {
+        float t = 0.0f;
+        #pragma unroll
+        for (int y = 0; y < 32; y++) t += part[y][threadIdx.x];
+        gbuf[col] = t;
+        if (col < nd.P) adam_one(nd, a, params, paramsT, m, v, t, (double)tstep, col, fm);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence();
+        if (atomicAdd(done_counter, 1u) == gridDim.x - 1) {
+            *done_counter = 0u;
+            __threadfence();
+            loss_record(nd, a, __ldcg(gbuf + nd.P), __ldcg(gbuf + nd.P + 1), __ldcg(gbuf + nd.P + 2), loss_out, flag);
+            *step = tstep;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -163,7 +239,7 @@ reduce_exchange_adam_kernel(const NetDims nd, const AdamArgs a, float* __restric
                             float* __restrict__ part_b, int rows_b, float* __restrict__ params,
                             float* __restrict__ paramsT, float* __restrict__ m, float* __restrict__ v,
                             float* __restrict__ gbuf, unsigned long long* __restrict__ step, unsigned long long tstep,
-                            float* __restrict__ loss_out, int* __restrict__ flag, const P2PArgs x) {
+                            float* __restrict__ loss_out, int* __restrict__ flag, const P2PArgs x, const FragMirror fm) {
     __shared__ float part[32][33];
     constexpr int RU = 8;
     const int PP = nd.PP, n_out = nd.P + 3;
@@ -224,7 +300,7 @@ reduce_exchange_adam_kernel(const NetDims nd, const AdamArgs a, float* __restric
         for (int r = 0; r < x.nranks; r++) g += __ldcv(mine + ((size_t)(r * 2 + par)) * PP + col);   // rank order, local reads
         gbuf[col] = g;
         if (col < nd.P) {
-            adam_one(nd, a, params, paramsT, m, v, g, (double)tstep, col);
+            adam_one(nd, a, params, paramsT, m, v, g, (double)tstep, col, fm);
         } else if (col == nd.P) {
             float s3[3];
             #pragma unroll
@@ -329,11 +405,17 @@ struct pinn_ctx {
     long long wq_term_stride = 0;
     uint8_t* d_ring = nullptr; long long ring_per_cta = 0; int tc_defer_g = 0;   // deferred dW (width 256)
     int tc_ut = 8, nterms = 0, tc_threads = 0, tc_smem = 0, tc_tmem_cols = 0, grid_cap_tc = 0;
+    // register-chained mma.sync kernel (width 20, PINN_PREC_BF16X3): interior set only
+    typedef void (*mma_fn)(const NetDims, const MmaArgs);
+    mma_fn kern_mma = nullptr;
+    uint32_t* d_wfrag = nullptr;
+    int grid_cap_mma = 0, mma_smem = 0, mma_terms = 0;
     AdamArgs adam{};
     void* comm = nullptr;
     // peer-memory exchange (fused reduce + all-reduce + Adam)
     float* d_xchg = nullptr; float* peer_ptr[kMaxP2PRanks] = {nullptr}; bool p2p_ready = false;
     unsigned long long xseq = 0; unsigned int* d_done = nullptr;
+    unsigned int* d_tail = nullptr;     // arrival counter of reduce_adam_kernel
     std::string err;
     // profiling
     bool prof = false;
@@ -530,11 +612,33 @@ static int configure_kernels(pinn_ctx* c) {
             c->kern_warp = nullptr;
         }
     }
+    // kernels of one step run concurrently (interior || boundary/initial): give them the SAME shared-memory carve-out, or an
+    // SM configured for one cannot take CTAs of the other until it drains (measured: the value launch serialised, +30 us)
+    CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_full, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_val, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (c->cfg.precision != PINN_PREC_FP32 && H == 20) {
+        // narrow net: register-chained mma.sync kernel for the interior set (boundary / initial points keep the FP32 kernel)
+        if ((c->cfg.precision != PINN_PREC_BF16X3 && c->cfg.precision != PINN_PREC_BF16X6) || nd.d_in != 2 || nd.n2 != 1 || nd.d_out != 1)
+            return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: at width 20 the tensor-core path is PINN_PREC_BF16X3 or PINN_PREC_BF16X6 for the 2 -> [20 x L] -> 1 Burgers network");
+        c->mma_terms = c->cfg.precision == PINN_PREC_BF16X6 ? 3 : 2;
+        c->kern_mma = c->mma_terms == 3 ? fused_step_mma<2, 1, 20, 3> : fused_step_mma<2, 1, 20, 2>;
+        c->mma_smem = kMmaWarps * 2 * nd.C * c->mma_terms * 768;
+        CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, c->mma_smem));
+        CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_mma, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int occ = 0;
+        CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->kern_mma, kMmaWarps * 32, c->mma_smem));
+        if (occ < 1) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: mma kernel does not fit on an SM");
+        c->grid_cap_mma = occ * c->num_sms;
+        c->kernel_id = 200 + c->mma_terms;
+        return PINN_OK;
+    }
+    if (c->cfg.precision == PINN_PREC_BF16X6)
+        return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: PINN_PREC_BF16X6 is built for width 20 (the 2 -> [20 x L] -> 1 Burgers network)");
     if (c->cfg.precision != PINN_PREC_FP32) {
         // tensor-core kernel for the interior set; boundary / initial points keep the FP32 kernel
         const int nterms = c->cfg.precision == PINN_PREC_BF16X3 ? 2 : 1;
         if (!(H == 64 || H == 128 || H == 256))
-            return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: the tensor-core path is built for width 64, 128 or 256 (use PINN_PREC_FP32)");
+            return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: the tensor-core path is built for width 20 (BF16X3), 64, 128 or 256 (use PINN_PREC_FP32)");
         const int ut = 8;
         c->tc_ut = ut;
 #define PICK_TC_H(D, N, HH) (nterms == 2 ? fused_step_tc<D, N, 2, 8, HH> : fused_step_tc<D, N, 1, 8, HH>)
@@ -646,6 +750,32 @@ static int launch_fused(pinn_ctx* c, cudaStream_t stream, bool full, const Point
     return PINN_OK;
 }
 
+// Width-20 mma.sync kernel: ONE launch walks the 16-point tiles of all three sets (interior tiles with every Taylor channel,
+// boundary / initial tiles value-only).  A second concurrent kernel would take resident-CTA slots away from it: its 400 CTAs
+// (C2) need 400 of the 444 register-limited slots, so any co-resident CTA pushes some of them into a second wave (+30 us).
+static int launch_mma(pinn_ctx* c, const PointSet& interior, const PointSet* vsets, int nv, int* rows_out) {
+    MmaArgs ma{};
+    ma.params = c->d_params; ma.wfrag = c->d_wfrag; ma.set = interior; ma.set.ntiles = tiles_of(interior.n, 16);
+    ma.nvsets = nv;
+    int total = ma.set.ntiles;
+    for (int i = 0; i < nv; i++) { ma.vsets[i] = vsets[i]; ma.vsets[i].ntiles = tiles_of(vsets[i].n, 16); total += ma.vsets[i].ntiles; }
+    ma.partial = c->d_partial; ma.stash = c->d_stash; ma.row0 = 0; ma.stash_per_row = c->stash_per_cta;
+    *rows_out = 0;
+    if (total == 0) return PINN_OK;
+    const int ctas = (total + kMmaWarps - 1) / kMmaWarps;
+    const int grid = ctas < c->grid_cap_mma ? ctas : c->grid_cap_mma;
+    const bool timed = c->prof && !c->capturing;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream); }
+    c->kern_mma<<<grid, kMmaWarps * 32, c->mma_smem, c->stream>>>(c->nd, ma);
+    if (timed) { cudaEventRecord(e1, c->stream); c->pending.emplace_back(e0, e1); }
+    c->last_grid = grid;
+    *rows_out = grid * kMmaWarps < total ? grid * kMmaWarps : total;   // one row per warp that owns at least one tile
+    c->step_launches++;
+    CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
+    return PINN_OK;
+}
+
 // Local part of a step: interior launch on the main stream, boundary + initial launch concurrently
 // on the auxiliary stream (disjoint partial rows), then the fixed-order reduction of all rows.
 static int run_local(pinn_ctx* c, int bump_step, bool do_reduce = true) {
@@ -655,16 +785,17 @@ static int run_local(pinn_ctx* c, int bump_step, bool do_reduce = true) {
         v[nv].x = c->d_x[k]; v[nv].n = c->n_local[k]; v[nv].scale = c->scale[k]; v[nv].set = k;
         v[nv].ntiles = tiles_of(c->n_local[k], c->val_TP); nv++;
     }
-    if (nv) {
+    const bool mk = c->kern_mma != nullptr;
+    if (nv && !mk) {
         CUDA_TRY(c, "pinn_train_step", cudaEventRecord(c->ev_fork, c->stream));
         CUDA_TRY(c, "pinn_train_step", cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
     }
     PointSet s{};
     s.x = c->d_x[0]; s.n = c->n_local[0]; s.scale = c->scale[0]; s.set = PINN_SET_INTERIOR; s.ntiles = tiles_of(s.n, c->TP);
     int grid_a = 0, grid_b = 0;
-    int rc = launch_fused(c, c->stream, true, &s, 1, 0, nullptr, nullptr, 0, &grid_a);
+    int rc = mk ? launch_mma(c, s, v, nv, &grid_a) : launch_fused(c, c->stream, true, &s, 1, 0, nullptr, nullptr, 0, &grid_a);
     if (rc) return rc;
-    if (nv) {
+    if (nv && !mk) {
         const int row0 = c->rows_cap_a;                   // rows [0, rows_cap_a) belong to the interior launch
         rc = launch_fused(c, c->stream2, false, v, nv, 0, nullptr, nullptr, row0, &grid_b);
         if (rc) return rc;
@@ -675,13 +806,31 @@ static int run_local(pinn_ctx* c, int bump_step, bool do_reduce = true) {
     if (!do_reduce) return PINN_OK;
     const int n_out = c->nd.P + 3;
     reduce_partials_kernel<<<(n_out + 31) / 32, dim3(32, 32), 0, c->stream>>>(
-        c->d_partial, grid_a, c->d_partial + (size_t)c->rows_cap_a * c->nd.PP, grid_b, c->nd.PP, n_out, c->d_gbuf, c->d_step, bump_step);
+        c->d_partial, grid_a, c->d_partial + (size_t)c->rows_cap_a * c->nd.PP, grid_b, c->nd.PP, n_out, c->d_gbuf, c->d_step, bump_step,
+        c->kern_mma ? 0 : 1);
     c->step_launches++;
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
     return PINN_OK;
 }
 
-static void refresh_wq(pinn_ctx* c);
+static void refresh_wq(pinn_ctx* c, bool after_adam = false);
+static FragMirror frag_mirror(const pinn_ctx* c) {
+    FragMirror fm{};
+    if (c->d_wfrag && c->nd.L >= 2) { fm.w16 = reinterpret_cast<unsigned short*>(c->d_wfrag); fm.nterms = c->mma_terms; }
+    return fm;
+}
+
+// Single-GPU tail of the step: reduce + Adam + mirrors + loss record in one launch.
+static int run_tail(pinn_ctx* c) {
+    const int n_out = c->nd.P + 3;
+    reduce_adam_kernel<<<(n_out + 31) / 32, dim3(32, 32), 0, c->stream>>>(
+        c->nd, c->adam, c->d_partial, c->rows_a, c->kern_mma ? 0 : 1, c->d_partial + (size_t)c->rows_cap_a * c->nd.PP, c->rows_b,
+        c->d_params, c->d_paramsT, c->d_m, c->d_v, c->d_gbuf, c->d_step, c->d_loss, c->d_flag, c->d_tail, frag_mirror(c));
+    c->step_launches++;
+    refresh_wq(c, true);
+    CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
+    return PINN_OK;
+}
 
 // Fused reduce + peer-memory all-reduce + Adam (see reduce_exchange_adam_kernel).
 static int run_exchange_apply(pinn_ctx* c) {
@@ -693,14 +842,19 @@ static int run_exchange_apply(pinn_ctx* c) {
     reduce_exchange_adam_kernel<<<(n_out + 31) / 32, dim3(32, 32), 0, c->stream>>>(
         c->nd, c->adam, c->d_partial, c->rows_a, c->d_partial + (size_t)c->rows_cap_a * c->nd.PP, c->rows_b,
         c->d_params, c->d_paramsT, c->d_m, c->d_v, c->d_gbuf, c->d_step, (unsigned long long)(c->host_step + 1),
-        c->d_loss, c->d_flag, x);
+        c->d_loss, c->d_flag, x, frag_mirror(c));
     c->step_launches++;
-    refresh_wq(c);
+    refresh_wq(c, true);
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
     return PINN_OK;
 }
 
-static void refresh_wq(pinn_ctx* c) {
+static void refresh_wq(pinn_ctx* c, bool after_adam) {
+    if (c->d_wfrag && c->nd.L >= 2 && !after_adam) {       // (the Adam kernels refresh this mirror themselves)
+        const int n = (c->nd.L - 1) * 2 * 9 * c->mma_terms * 32;
+        pack_wfrag_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->nd, c->d_params, c->d_wfrag, c->mma_terms);
+        c->step_launches++;
+    }
     if (!c->d_wq) return;
     const long long n = c->wq_term_stride;
     pack_wq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->nd, c->d_params, c->d_wq, c->wq_term_stride, c->nterms);
@@ -717,16 +871,18 @@ static int run_allreduce(pinn_ctx* c) {
 
 static int run_apply(pinn_ctx* c, int apply) {
     adam_kernel<<<(c->nd.P + 255) / 256, 256, 0, c->stream>>>(c->nd, c->adam, c->d_params, c->d_paramsT, c->d_m, c->d_v,
-                                                            c->d_gbuf, c->d_step, c->d_loss, c->d_flag, apply);
+                                                            c->d_gbuf, c->d_step, c->d_loss, c->d_flag, apply, frag_mirror(c));
     c->step_launches++;
-    if (apply) refresh_wq(c);
+    if (apply) refresh_wq(c, true);
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
     return PINN_OK;
 }
 
 // All device work of one training step, issued on the handle's streams (directly, or under capture).
 static int issue_step(pinn_ctx* c) {
-    const bool p2p = c->cfg.nranks > 1 && c->comm != nullptr && c->p2p_ready;
+    const bool dist = c->cfg.nranks > 1 && c->comm != nullptr;
+    const bool p2p = dist && c->p2p_ready;
+    if (!dist) { const int rc0 = run_local(c, 0, false); return rc0 ? rc0 : run_tail(c); }
     int rc = run_local(c, 1, !p2p);
     if (p2p) return rc ? rc : run_exchange_apply(c);
     if (!rc) rc = run_allreduce(c);
@@ -757,8 +913,8 @@ static int step_once(pinn_ctx* c) {
             cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
             int rc = PINN_ERR_CUDA;
             if (e == cudaSuccess) {
-                rc = run_local(c, 1, !p2p);               // with the peer exchange the reduction is part of the fused kernel
-                if (!rc && !dist) rc = run_apply(c, 1);
+                if (!dist) { rc = run_local(c, 0, false); if (!rc) rc = run_tail(c); }     // single GPU: the whole step
+                else rc = run_local(c, 1, !p2p);          // with the peer exchange the reduction is part of the fused kernel
             }
             cudaGraph_t g = nullptr;
             if (e == cudaSuccess) e = cudaStreamEndCapture(c->stream, &g);
@@ -828,7 +984,7 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     *out = nullptr;
     if (cfg->abi_version != PINN_ABI_VERSION) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: abi_version mismatch");
     if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: invalid rank / nranks");
-    if (cfg->precision < PINN_PREC_FP32 || cfg->precision > PINN_PREC_BF16) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: unknown precision");
+    if (cfg->precision < PINN_PREC_FP32 || cfg->precision > PINN_PREC_BF16X6) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: unknown precision");
     NetDims nd; std::string why;
     if (!make_dims(cfg, &nd, why)) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: " + why);
     int ndev = 0;
@@ -872,11 +1028,14 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     c->rows_cap_a = c->grid_cap_full > c->grid_cap_tc ? c->grid_cap_full : c->grid_cap_tc;
     if (c->grid_cap_val > c->rows_cap_a) c->rows_cap_a = c->grid_cap_val;      // pinn_forward uses the value kernel on rows A
     if (c->kern_warp && c->num_sms * c->warp_wpc > c->rows_cap_a) c->rows_cap_a = c->num_sms * c->warp_wpc;
+    if (c->kern_mma && c->grid_cap_mma * kMmaWarps > c->rows_cap_a) c->rows_cap_a = c->grid_cap_mma * kMmaWarps;
     c->rows_cap_b = c->grid_cap_val > c->grid_cap_tc ? c->grid_cap_val : c->grid_cap_tc;
     const size_t nrows = (size_t)c->rows_cap_a + c->rows_cap_b;
     c->stash_per_cta = (long long)nd.L * nd.C * nd.H * c->TP;   // the tensor-core kernel (16-point tiles) needs no more
     if ((long long)nd.L * nd.H * c->val_TP > c->stash_per_cta) c->stash_per_cta = (long long)nd.L * nd.H * c->val_TP;
     if (c->kern_tc_val && (long long)nd.L * 8 * nd.H * 16 > c->stash_per_cta) c->stash_per_cta = (long long)nd.L * 8 * nd.H * 16;
+    if (c->kern_mma && (long long)nd.L * nd.C * 3 * 128 > c->stash_per_cta) c->stash_per_cta = (long long)nd.L * nd.C * 3 * 128;
+    if (c->kern_mma) TRY_C(cudaMalloc(&c->d_wfrag, (size_t)(nd.L > 1 ? nd.L - 1 : 1) * 2 * 27 * 32 * sizeof(uint32_t)));
     const size_t P = nd.P;
     TRY_C(cudaMalloc(&c->d_params, (P + 4) * sizeof(float)));     // +4: kernels copy them in float4 units
     TRY_C(cudaMalloc(&c->d_paramsT, (P + 4) * sizeof(float)));
@@ -894,6 +1053,8 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     if (c->tc_defer_g > 0) TRY_C(cudaMalloc(&c->d_ring, (size_t)c->grid_cap_tc * c->ring_per_cta));
     TRY_C(cudaMalloc(&c->d_loss, 8 * sizeof(float)));          // [0..3] loss record, [4] overflow flag word: one D2H copy per read-back
     TRY_C(cudaMalloc(&c->d_step, sizeof(unsigned long long)));
+    TRY_C(cudaMalloc(&c->d_tail, sizeof(unsigned int)));
+    TRY_C(cudaMemsetAsync(c->d_tail, 0, sizeof(unsigned int), c->stream));
     c->d_flag = reinterpret_cast<int*>(c->d_loss + 4);
     TRY_C(cudaMallocHost(&c->h_pinned, 8 * sizeof(float)));
     TRY_C(cudaMemsetAsync(c->d_m, 0, P * sizeof(float), c->stream));
@@ -923,10 +1084,10 @@ void pinn_destroy(pinn_ctx* c) {
     for (int k = 0; k < 3; k++) cudaFree(c->d_x[k]);
     cudaFree(c->d_params); cudaFree(c->d_paramsT); cudaFree(c->d_m); cudaFree(c->d_v);
     cudaFree(c->d_gbuf); cudaFree(c->d_partial); cudaFree(c->d_stash); cudaFree(c->d_loss);
-    cudaFree(c->d_step); cudaFree(c->d_wq); cudaFree(c->d_ring);
+    cudaFree(c->d_step); cudaFree(c->d_wq); cudaFree(c->d_ring); cudaFree(c->d_wfrag);
     for (int r = 0; r < kMaxP2PRanks; r++)
         if (c->peer_ptr[r] && c->peer_ptr[r] != c->d_xchg) cudaIpcCloseMemHandle(c->peer_ptr[r]);
-    cudaFree(c->d_xchg); cudaFree(c->d_done);
+    cudaFree(c->d_xchg); cudaFree(c->d_done); cudaFree(c->d_tail);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     drop_graph(c);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
