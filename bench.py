@@ -236,7 +236,7 @@ def main():
     ap.add_argument("--points", type=int, default=0, help="interior points per GPU (default: the config's)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("PINN_BENCH_PRECISION", "auto"),
-                    choices=["auto", "fp32", "bf16x3", "bf16", "bf16x6"],
+                    choices=["auto", "fp32", "bf16x3", "bf16", "bf16x6", "fp16x3"],
                     help="contraction arithmetic: fp32 CUDA cores | bf16x3 / bf16 tcgen05 (width 64/128/256); "
                          "auto = fp32 for width < 64, bf16x3 for 64/128, bf16 for 256")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -273,9 +273,9 @@ def main():
     width = {1: 20, 2: 20, 3: 64, 4: 128, 5: 256}[which]
     prec_name = args.precision
     if prec_name == "auto":
-        # width 20 Burgers (C1, C2): FP32-equivalent 3-term split on mma.sync; other narrow nets: FP32 CUDA cores
-        prec_name = ("bf16x6" if which in (1, 2) and width == 20 else "fp32") if width < 64 else ("bf16x3" if width <= 128 else "bf16")
-    prec = {"fp32": P.PREC_FP32, "bf16x3": P.PREC_BF16X3, "bf16": P.PREC_BF16, "bf16x6": P.PREC_BF16X6}[prec_name]
+        # width 20 Burgers (C1, C2): FP32-grade scaled 2-term FP16 split on mma.sync (meets the FP32 path's bars); other narrow nets: FP32 CUDA cores
+        prec_name = ("fp16x3" if which in (1, 2) and width == 20 else "fp32") if width < 64 else ("bf16x3" if width <= 128 else "bf16")
+    prec = {"fp32": P.PREC_FP32, "bf16x3": P.PREC_BF16X3, "bf16": P.PREC_BF16, "bf16x6": P.PREC_BF16X6, "fp16x3": P.PREC_FP16X3}[prec_name]
     cfg = P.default_config(which, n_interior=nf, n_boundary=nb, n_initial=n0, rank=rank, nranks=world,
                            device=local_rank, precision=prec)
     net = P.Network(cfg)
@@ -360,7 +360,7 @@ def main():
         n_loc0 = net.local_count(0)
         ach_tf = n_loc0 * flops_pt / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
         ach_gb = n_loc0 * bytes_pt / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-        narrow_mma = prof["kernel_id"] in (202, 203)      # register-chained mma.sync kernel (width 20)
+        narrow_mma = prof["kernel_id"] in (202, 203, 204)      # register-chained mma.sync kernel (width 20)
         tensor_path = prec_name != "fp32" and not narrow_mma
         mma_mult = 3 if prec_name == "bf16x3" else 1     # issued tensor FLOPs per algorithmic FLOP
         if narrow_mma:
@@ -393,7 +393,9 @@ def main():
             "metric": "collocation points/sec per train step (fwd+residual+bwd+Adam)",
             "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16x6": "f32-equivalent: operands split into 3 bf16 terms (exact 24-bit split), 6 mma.sync products, "
+            "dtype": {"fp32": "f32", "fp16x3": "f32-equivalent: operands scaled by an exact power of two and split into 2 fp16 terms (22 bits), "
+                                               "3 mma.sync products, f32 accumulate + f32 elementwise",
+                      "bf16x6": "f32-equivalent: operands split into 3 bf16 terms (exact 24-bit split), 6 mma.sync products, "
                                                "f32 accumulate + f32 elementwise",
                       "bf16x3": "bf16x3 operands (2-term split), f32 accumulate + f32 elementwise",
                       "bf16": "bf16 operands, f32 accumulate + f32 elementwise"}[prec_name], "data": "synthetic",

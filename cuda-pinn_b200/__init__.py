@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libpinn_b200.so")
 
 PDE_BURGERS, PDE_HELMHOLTZ, PDE_ALLEN_CAHN, PDE_NAVIER_STOKES, PDE_HEAT = 0, 1, 2, 3, 4
 SET_INTERIOR, SET_BOUNDARY, SET_INITIAL = 0, 1, 2
-PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_BF16X6 = 0, 1, 2, 3
+PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_BF16X6, PREC_FP16X3 = 0, 1, 2, 3, 4
 ABI_VERSION = 1
 
 

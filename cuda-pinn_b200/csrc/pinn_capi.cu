@@ -83,12 +83,13 @@ struct AdamArgs {
 
 // Fragment-ordered BF16 mirror of the width-20 mma.sync kernel (pinn_fused_mma.cuh, layout of pack_wfrag_kernel),
 // viewed as 16-bit halves; w16 == nullptr: the handle has none.
-struct FragMirror { unsigned short* w16; int nterms; };
+struct FragMirror { unsigned short* w16; int nterms; int f16; };
 
 // the BF16 terms of hidden->hidden weight W_l[k][j] into both directions of the mirror
 __device__ __forceinline__ void frag_mirror_store(const FragMirror& fm, int l, int k, int j, float w) {
     uint32_t f[3];
-    split_pair<3>(w, 0.0f, f);                              // low halves: hi, mid, lo of w
+    if (fm.f16) { uint32_t h[2]; split_pair_f16(w * (float)(1 << kF16WeightShift), 0.0f, h); f[0] = h[0]; f[1] = h[1]; f[2] = 0u; }
+    else split_pair<3>(w, 0.0f, f);                         // low halves: hi, mid, lo of w
     const int words = 9 * fm.nterms;
     #pragma unroll
     for (int dir = 0; dir < 2; dir++) {
@@ -409,7 +410,7 @@ struct pinn_ctx {
     typedef void (*mma_fn)(const NetDims, const MmaArgs);
     mma_fn kern_mma = nullptr;
     uint32_t* d_wfrag = nullptr;
-    int grid_cap_mma = 0, mma_smem = 0, mma_terms = 0;
+    int grid_cap_mma = 0, mma_smem = 0, mma_terms = 0, mma_f16 = 0;
     AdamArgs adam{};
     void* comm = nullptr;
     // peer-memory exchange (fused reduce + all-reduce + Adam)
@@ -618,10 +619,11 @@ static int configure_kernels(pinn_ctx* c) {
     CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_val, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (c->cfg.precision != PINN_PREC_FP32 && H == 20) {
         // narrow net: register-chained mma.sync kernel for the interior set (boundary / initial points keep the FP32 kernel)
-        if ((c->cfg.precision != PINN_PREC_BF16X3 && c->cfg.precision != PINN_PREC_BF16X6) || nd.d_in != 2 || nd.n2 != 1 || nd.d_out != 1)
-            return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: at width 20 the tensor-core path is PINN_PREC_BF16X3 or PINN_PREC_BF16X6 for the 2 -> [20 x L] -> 1 Burgers network");
+        if (c->cfg.precision == PINN_PREC_BF16 || nd.d_in != 2 || nd.n2 != 1 || nd.d_out != 1)
+            return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: at width 20 the tensor-core path is PINN_PREC_BF16X3, PINN_PREC_BF16X6 or PINN_PREC_FP16X3 for the 2 -> [20 x L] -> 1 Burgers network");
         c->mma_terms = c->cfg.precision == PINN_PREC_BF16X6 ? 3 : 2;
-        c->kern_mma = c->mma_terms == 3 ? fused_step_mma<2, 1, 20, 3> : fused_step_mma<2, 1, 20, 2>;
+        c->mma_f16 = c->cfg.precision == PINN_PREC_FP16X3 ? 1 : 0;
+        c->kern_mma = c->mma_f16 ? fused_step_mma<2, 1, 20, 2, true> : (c->mma_terms == 3 ? fused_step_mma<2, 1, 20, 3> : fused_step_mma<2, 1, 20, 2>);
         c->mma_smem = kMmaWarps * 2 * nd.C * c->mma_terms * 768;
         CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, c->mma_smem));
         CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_mma, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -629,11 +631,11 @@ static int configure_kernels(pinn_ctx* c) {
         CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->kern_mma, kMmaWarps * 32, c->mma_smem));
         if (occ < 1) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: mma kernel does not fit on an SM");
         c->grid_cap_mma = occ * c->num_sms;
-        c->kernel_id = 200 + c->mma_terms;
+        c->kernel_id = c->mma_f16 ? 204 : 200 + c->mma_terms;
         return PINN_OK;
     }
-    if (c->cfg.precision == PINN_PREC_BF16X6)
-        return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: PINN_PREC_BF16X6 is built for width 20 (the 2 -> [20 x L] -> 1 Burgers network)");
+    if (c->cfg.precision == PINN_PREC_BF16X6 || c->cfg.precision == PINN_PREC_FP16X3)
+        return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: PINN_PREC_BF16X6 / PINN_PREC_FP16X3 are built for width 20 (the 2 -> [20 x L] -> 1 Burgers network)");
     if (c->cfg.precision != PINN_PREC_FP32) {
         // tensor-core kernel for the interior set; boundary / initial points keep the FP32 kernel
         const int nterms = c->cfg.precision == PINN_PREC_BF16X3 ? 2 : 1;
@@ -816,7 +818,7 @@ static int run_local(pinn_ctx* c, int bump_step, bool do_reduce = true) {
 static void refresh_wq(pinn_ctx* c, bool after_adam = false);
 static FragMirror frag_mirror(const pinn_ctx* c) {
     FragMirror fm{};
-    if (c->d_wfrag && c->nd.L >= 2) { fm.w16 = reinterpret_cast<unsigned short*>(c->d_wfrag); fm.nterms = c->mma_terms; }
+    if (c->d_wfrag && c->nd.L >= 2) { fm.w16 = reinterpret_cast<unsigned short*>(c->d_wfrag); fm.nterms = c->mma_terms; fm.f16 = c->mma_f16; }
     return fm;
 }
 
@@ -852,7 +854,7 @@ static int run_exchange_apply(pinn_ctx* c) {
 static void refresh_wq(pinn_ctx* c, bool after_adam) {
     if (c->d_wfrag && c->nd.L >= 2 && !after_adam) {       // (the Adam kernels refresh this mirror themselves)
         const int n = (c->nd.L - 1) * 2 * 9 * c->mma_terms * 32;
-        pack_wfrag_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->nd, c->d_params, c->d_wfrag, c->mma_terms);
+        pack_wfrag_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->nd, c->d_params, c->d_wfrag, c->mma_terms, c->mma_f16);
         c->step_launches++;
     }
     if (!c->d_wq) return;
@@ -984,7 +986,7 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     *out = nullptr;
     if (cfg->abi_version != PINN_ABI_VERSION) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: abi_version mismatch");
     if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: invalid rank / nranks");
-    if (cfg->precision < PINN_PREC_FP32 || cfg->precision > PINN_PREC_BF16X6) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: unknown precision");
+    if (cfg->precision < PINN_PREC_FP32 || cfg->precision > PINN_PREC_FP16X3) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: unknown precision");
     NetDims nd; std::string why;
     if (!make_dims(cfg, &nd, why)) return fail(nullptr, PINN_ERR_INVALID_ARGUMENT, "pinn_create: " + why);
     int ndev = 0;
@@ -1034,7 +1036,7 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     c->stash_per_cta = (long long)nd.L * nd.C * nd.H * c->TP;   // the tensor-core kernel (16-point tiles) needs no more
     if ((long long)nd.L * nd.H * c->val_TP > c->stash_per_cta) c->stash_per_cta = (long long)nd.L * nd.H * c->val_TP;
     if (c->kern_tc_val && (long long)nd.L * 8 * nd.H * 16 > c->stash_per_cta) c->stash_per_cta = (long long)nd.L * 8 * nd.H * 16;
-    if (c->kern_mma && (long long)nd.L * nd.C * 3 * 128 > c->stash_per_cta) c->stash_per_cta = (long long)nd.L * nd.C * 3 * 128;
+    if (c->kern_mma && (long long)nd.L * (nd.C * 3 * 128 + 32) > c->stash_per_cta) c->stash_per_cta = (long long)nd.L * (nd.C * 3 * 128 + 32);
     if (c->kern_mma) TRY_C(cudaMalloc(&c->d_wfrag, (size_t)(nd.L > 1 ? nd.L - 1 : 1) * 2 * 27 * 32 * sizeof(uint32_t)));
     const size_t P = nd.P;
     TRY_C(cudaMalloc(&c->d_params, (P + 4) * sizeof(float)));     // +4: kernels copy them in float4 units

@@ -28,6 +28,7 @@
 #pragma once
 #include <type_traits>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "pinn_device.cuh"
 #include "pinn_fused_fp32.cuh"
 
@@ -65,6 +66,38 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t (&f)[NTE
         if (k + 1 < NTERMS) { x0 -= __uint_as_float(f[k] << 16); x1 -= __uint_as_float(f[k] & 0xffff0000u); }
     }
 }
+// FP16 flavour (PINN_PREC_FP16X3): two FP16 terms carry 22 significand bits, so three MMAs give near-FP32 products at the
+// cost of the two-term BF16 split.  FP16 has a 5-bit exponent, so every operand fragment is first multiplied by an exact
+// power of two chosen per warp and channel from the fragment's largest magnitude (results are scaled back exactly).
+constexpr int kF16WeightShift = 4;                // the weight mirror holds W * 2^4
+constexpr int kF16TargetExp = 13;                 // scaled fragment maximum lies in [2^13, 2^14)
+__device__ __forceinline__ void mma16816_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma1688_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ void split_pair_f16(float x0, float x1, uint32_t (&f)[2]) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(f[0]) : "f"(x1), "f"(x0));
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&f[0]));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(f[1]) : "f"(x1 - h.y), "f"(x0 - h.x));
+}
+// power-of-two shift k (scale 2^k) that brings a fragment whose largest magnitude is `m` to [2^13, 2^14); clamped to
+// [-17, 43] (magnitudes in [2^-30, 2^30] keep full precision) so that sums of two shifts stay representable
+__device__ __forceinline__ int f16_shift(float m) {
+    int e = (int)((__float_as_uint(m) >> 23) & 0xffu);
+    e = e < 97 ? 97 : (e > 157 ? 157 : e);
+    return kF16TargetExp + 127 - e;
+}
+__device__ __forceinline__ float pow2i(int k) { return __uint_as_float((uint32_t)(127 + k) << 23); }
+__device__ __forceinline__ float warp_max(float m) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    return m;
+}
+
 // cross terms (A term, B term) kept by the NTERMS-term product, smallest first
 template <int NTERMS> struct TermPairs {
     static constexpr int n = NTERMS == 3 ? 6 : 3;
@@ -92,7 +125,7 @@ __device__ __forceinline__ float sum_over_g(float v) {
 // idx = (nt*nterms + term)*3 + r holds B[k0][n], B[k0+1][n] (low, high half) for n = 8nt + g and
 // k0 = 2t (r=0, k16 b0) | 2t+8 (r=1, k16 b1) | 16+2t (r=2, k8 b0);  dir 0: B[k][n] = W[k][n] (forward),
 // dir 1: B[k][n] = W[n][k] (dA = Zbar W^T).  Entries outside the H x H matrix are zero.
-__global__ void pack_wfrag_kernel(const NetDims nd, const float* __restrict__ params, uint32_t* __restrict__ wfrag, int nterms) {
+__global__ void pack_wfrag_kernel(const NetDims nd, const float* __restrict__ params, uint32_t* __restrict__ wfrag, int nterms, int f16) {
     const int words = 9 * nterms;
     const int total = (nd.L - 1) * 2 * words * 32;
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,13 +141,14 @@ __global__ void pack_wfrag_kernel(const NetDims nd, const float* __restrict__ pa
         x[e] = (k < H && n < H) ? (dir == 0 ? W[k * H + n] : W[n * H + k]) : 0.0f;
     }
     uint32_t f[3];
-    split_pair<3>(x[0], x[1], f);
+    if (f16) { uint32_t h[2]; split_pair_f16(x[0] * (float)(1 << kF16WeightShift), x[1] * (float)(1 << kF16WeightShift), h); f[0] = h[0]; f[1] = h[1]; f[2] = 0u; }
+    else split_pair<3>(x[0], x[1], f);
     wfrag[w] = f[term];
 }
 
 // One 16-point tile on one warp.  VAL = false: interior tile, all NC Taylor channels, PDE residual.
 // VAL = true: boundary / initial tile, value channel only, Dirichlet / initial target (same fragment schedule with NC = 1).
-template <int DIN, int N2, int HT, int NTERMS, bool VAL>
+template <int DIN, int N2, int HT, int NTERMS, bool VAL, bool F16>
 __device__ __forceinline__ void mma_tile(const NetDims& nd, const MmaArgs& args, const PointSet& ps, int tile, uint32_t* sbuf,
                                          float* part, float4* stash, bool first) {
     constexpr int ND = VAL ? 0 : DIN, NS = VAL ? 0 : N2;   // tangent channels carried
@@ -122,12 +156,26 @@ __device__ __forceinline__ void mma_tile(const NetDims& nd, const MmaArgs& args,
     constexpr int NCS = 1 + DIN + N2;                     // channel stride of the shared buffer (sized for interior tiles)
     constexpr int WORDS = 9 * NTERMS;                     // fragment words per (layer, direction)
     using TP = TermPairs<NTERMS>;
+    static_assert(!F16 || NTERMS == 2, "the FP16 flavour is a two-term split");
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int L = nd.L;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sbuf);
     // gradient output: the warp's FIRST tile stores (its row needs no zeroing), later tiles add by fire-and-forget RED
     auto emit = [&](float* p, float val) { if (first) *p = val; else red_add(p, val); };
+    auto mma_k16 = [](float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+        if constexpr (F16) mma16816_f16(d, a0, a1, a2, a3, b0, b1); else mma16816(d, a0, a1, a2, a3, b0, b1);
+    };
+    auto mma_k8 = [](float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+        if constexpr (F16) mma1688_f16(d, a0, a1, b0); else mma1688(d, a0, a1, b0);
+    };
+    auto split = [](float x0, float x1, uint32_t (&f)[NTERMS]) {
+        if constexpr (F16) split_pair_f16(x0, x1, f); else split_pair<NTERMS>(x0, x1, f);
+    };
+    // FP16 flavour: power-of-two shift of the last chain_gemm's input fragment per channel (dW needs the Zbar ones), and
+    // the per-layer word of forward shifts kept in the stash (byte c = shift of A_{l-1,c} + 64)
+    int kin[NC];
+    uint32_t* stash_exp = reinterpret_cast<uint32_t*>(stash) + (size_t)nd.L * NCS * NT * 128;
 
     // unit index of fragment slot (nt, e) and its validity
     int ju[NT][2]; bool jv[NT][2];
@@ -183,12 +231,22 @@ __device__ __forceinline__ void mma_tile(const NetDims& nd, const MmaArgs& args,
                 for (int r = 0; r < 3; r++) b[nt][k][r] = __ldg(wf + ((nt * NTERMS + k) * 3 + r) * 32);
         #pragma unroll
         for (int c = 0; c < NC; c++) {
+            float sc = 1.0f;
+            if constexpr (F16) {                            // exact power-of-two scaling of this channel's fragment
+                float mx = 0.0f;
+                #pragma unroll
+                for (int nt = 0; nt < NT; nt++)
+                    #pragma unroll
+                    for (int q = 0; q < 4; q++) mx = fmaxf(mx, fabsf(v[c][nt][q]));
+                kin[c] = f16_shift(warp_max(mx));
+                sc = pow2i(kin[c]);
+            }
             uint32_t f[6][NTERMS];                          // slot nt*2+h = (rows g+8h, columns of n-tile nt)
             #pragma unroll
             for (int nt = 0; nt < NT; nt++)
                 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    split_pair<NTERMS>(v[c][nt][2 * h], v[c][nt][2 * h + 1], f[nt * 2 + h]);
+                    split(v[c][nt][2 * h] * sc, v[c][nt][2 * h + 1] * sc, f[nt * 2 + h]);
                     if constexpr (STORE) {
                         const int word = (g + 8 * h) * 12 + 4 * nt + t;
                         #pragma unroll
@@ -202,17 +260,31 @@ __device__ __forceinline__ void mma_tile(const NetDims& nd, const MmaArgs& args,
             for (int q = 0; q + 1 < TP::n; q += 2)
                 #pragma unroll
                 for (int nt = 0; nt < NT; nt++)
-                    mma16816(v[c][nt], f[4][TP::a(q)], f[5][TP::a(q)], f[4][TP::a(q + 1)], f[5][TP::a(q + 1)],
-                             b[nt][TP::b(q)][2], b[nt][TP::b(q + 1)][2]);
+                    mma_k16(v[c][nt], f[4][TP::a(q)], f[5][TP::a(q)], f[4][TP::a(q + 1)], f[5][TP::a(q + 1)],
+                            b[nt][TP::b(q)][2], b[nt][TP::b(q + 1)][2]);
             if constexpr (TP::n & 1) {
                 #pragma unroll
-                for (int nt = 0; nt < NT; nt++) mma1688(v[c][nt], f[4][TP::a(TP::n - 1)], f[5][TP::a(TP::n - 1)], b[nt][TP::b(TP::n - 1)][2]);
+                for (int nt = 0; nt < NT; nt++) mma_k8(v[c][nt], f[4][TP::a(TP::n - 1)], f[5][TP::a(TP::n - 1)], b[nt][TP::b(TP::n - 1)][2]);
             }
             #pragma unroll
             for (int q = 0; q < TP::n; q++)                 // units 0..15; the three n-tiles are independent accumulators
                 #pragma unroll
                 for (int nt = 0; nt < NT; nt++)
-                    mma16816(v[c][nt], f[0][TP::a(q)], f[1][TP::a(q)], f[2][TP::a(q)], f[3][TP::a(q)], b[nt][TP::b(q)][0], b[nt][TP::b(q)][1]);
+                    mma_k16(v[c][nt], f[0][TP::a(q)], f[1][TP::a(q)], f[2][TP::a(q)], f[3][TP::a(q)], b[nt][TP::b(q)][0], b[nt][TP::b(q)][1]);
+            if constexpr (F16) {
+                const float us = pow2i(-(kin[c] + kF16WeightShift));
+                #pragma unroll
+                for (int nt = 0; nt < NT; nt++)
+                    #pragma unroll
+                    for (int q = 0; q < 4; q++) v[c][nt][q] *= us;
+            }
+        }
+        if constexpr (F16 && !STORE) {                      // forward: the shifts of A_{l-1}, needed again for dW_l
+            static_assert(NC <= 4, "one byte per channel");
+            uint32_t w = 0;
+            #pragma unroll
+            for (int c = 0; c < NC; c++) w |= (uint32_t)(kin[c] + 64) << (8 * c);
+            stash_exp[(size_t)(l - 1) * 32 + lane] = w;
         }
     };
 
@@ -383,6 +455,21 @@ __device__ __forceinline__ void mma_tile(const NetDims& nd, const MmaArgs& args,
             break;
         }
         chain_gemm(l, 1, std::true_type{});                // Zbar_l terms -> shared buffer 1;  v = Abar_{l-1} = Zbar_l W_l^T
+        // FP16 flavour: give A_{l-1,c} the shift K - shift(Zbar_c), K = min_c(own best shift + shift(Zbar_c)): every channel's
+        // products then carry 2^K and share one dW accumulator; the channel that dominates dW keeps full precision
+        float sa[NC];
+        int K = 0;
+        if constexpr (F16) {
+            const uint32_t w = stash_exp[(size_t)(l - 1) * 32 + lane];
+            K = 1 << 20;
+            #pragma unroll
+            for (int c = 0; c < NC; c++) { const int kopt = (int)((w >> (8 * c)) & 0xffu) - 64; K = min(K, kopt + kin[c]); }
+            #pragma unroll
+            for (int c = 0; c < NC; c++) sa[c] = pow2i(K - kin[c]);
+        } else {
+            #pragma unroll
+            for (int c = 0; c < NC; c++) sa[c] = 1.0f;
+        }
         // A_{l-1} (the other dW operand) recomputed from the stash of layer l-1, straight into shared buffer 0
         #pragma unroll
         for (int nt = 0; nt < NT; nt++) {
@@ -409,7 +496,8 @@ __device__ __forceinline__ void mma_tile(const NetDims& nd, const MmaArgs& args,
                 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     uint32_t f[NTERMS];
-                    split_pair<NTERMS>(ac[c][2 * h], ac[c][2 * h + 1], f);
+                    if constexpr (F16) split(ac[c][2 * h] * sa[c], ac[c][2 * h + 1] * sa[c], f);
+                    else split(ac[c][2 * h], ac[c][2 * h + 1], f);
                     const int word = (g + 8 * h) * 12 + 4 * nt + t;
                     #pragma unroll
                     for (int k = 0; k < NTERMS; k++) sbuf[((0 * NCS + c) * NTERMS + k) * 192 + word] = f[k];
@@ -445,8 +533,8 @@ __device__ __forceinline__ void mma_tile(const NetDims& nd, const MmaArgs& args,
             for (int q = 0; q < TP::n; q++)                 // units i = 0..15
                 #pragma unroll
                 for (int nt = 0; nt < NT; nt++)
-                    mma16816(dw[0][nt], a0[TP::a(q)][0], a0[TP::a(q)][1], a0[TP::a(q)][2], a0[TP::a(q)][3],
-                             bfrag(nt, TP::b(q), 0), bfrag(nt, TP::b(q), 1));
+                    mma_k16(dw[0][nt], a0[TP::a(q)][0], a0[TP::a(q)][1], a0[TP::a(q)][2], a0[TP::a(q)][3],
+                            bfrag(nt, TP::b(q), 0), bfrag(nt, TP::b(q), 1));
             // units i = 16..19 fill only rows 0..7 of their m16 tile: rows 8..15 take a SECOND A term that meets the same
             // B term (A terms ka with ka + kb <= NTERMS - 1), and are folded into rows 0..7 after the channel loop
             #pragma unroll
@@ -456,25 +544,26 @@ __device__ __forceinline__ void mma_tile(const NetDims& nd, const MmaArgs& args,
                     #pragma unroll
                     for (int nt = 0; nt < NT; nt++) {
                         const bool two = ka + 1 + kb < NTERMS;
-                        mma16816(dw[1][nt], a1[ka][0], two ? a1[ka + 1][0] : 0u, a1[ka][1], two ? a1[ka + 1][1] : 0u,
-                                 bfrag(nt, kb, 0), bfrag(nt, kb, 1));
+                        mma_k16(dw[1][nt], a1[ka][0], two ? a1[ka + 1][0] : 0u, a1[ka][1], two ? a1[ka + 1][1] : 0u,
+                                bfrag(nt, kb, 0), bfrag(nt, kb, 1));
                     }
         }
         __syncwarp();                                       // buffer reads done before the next layer overwrites it
+        const float usw = F16 ? pow2i(-K) : 1.0f;
         #pragma unroll
         for (int nt = 0; nt < NT; nt++)
             #pragma unroll
             for (int e = 0; e < 2; e++) {
                 if (!jv[nt][e]) continue;
                 float* col = part + nd.offW[l] + ju[nt][e];
-                emit(col + (g) * HT, dw[0][nt][e]);
-                emit(col + (g + 8) * HT, dw[0][nt][2 + e]);
-                if (g < HT - 16) emit(col + (16 + g) * HT, dw[1][nt][e] + dw[1][nt][2 + e]);
+                emit(col + (g) * HT, dw[0][nt][e] * usw);
+                emit(col + (g + 8) * HT, dw[0][nt][2 + e] * usw);
+                if (g < HT - 16) emit(col + (16 + g) * HT, (dw[1][nt][e] + dw[1][nt][2 + e]) * usw);
             }
     }
 }
 
-template <int DIN, int N2, int HT, int NTERMS>
+template <int DIN, int N2, int HT, int NTERMS, bool F16 = false>
 __global__ void __launch_bounds__(kMmaWarps * 32, 3)
 fused_step_mma(const NetDims nd, const MmaArgs args) {
     static_assert(HT == 20, "fragment schedule: one k16 step + an 8-wide remainder, three n8 tiles");
@@ -493,11 +582,11 @@ fused_step_mma(const NetDims nd, const MmaArgs args) {
     bool first = true;
     for (int tile = blockIdx.x * kMmaWarps + warp; tile < total; tile += gridDim.x * kMmaWarps) {
         if (tile < n_full) {
-            mma_tile<DIN, N2, HT, NTERMS, false>(nd, args, args.set, tile, sbuf, part, stash, first);
+            mma_tile<DIN, N2, HT, NTERMS, false, F16>(nd, args, args.set, tile, sbuf, part, stash, first);
         } else {
             const bool second = tile >= n_full + n_v0;
             const PointSet ps = second ? args.vsets[1] : args.vsets[0];
-            mma_tile<DIN, N2, HT, NTERMS, true>(nd, args, ps, tile - n_full - (second ? n_v0 : 0), sbuf, part, stash, first);
+            mma_tile<DIN, N2, HT, NTERMS, true, F16>(nd, args, ps, tile - n_full - (second ? n_v0 : 0), sbuf, part, stash, first);
         }
         first = false;
     }

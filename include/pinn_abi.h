@@ -73,10 +73,13 @@ typedef enum pinn_precision {
     PINN_PREC_BF16X3 = 1, /* tcgen05 kind::f16, each operand split into two BF16 terms (hi*hi + hi*mid +
                              mid*hi), FP32 accumulate in TMEM: near-FP32 products; width 64 or 128 */
     PINN_PREC_BF16   = 2, /* tcgen05 kind::f16, BF16 operands, FP32 accumulate in TMEM; width 64/128/256 */
-    PINN_PREC_BF16X6 = 3  /* width 20 (2 -> [20 x L] -> 1): warp-level mma.sync, each operand split into THREE BF16 terms
+    PINN_PREC_BF16X6 = 3, /* width 20 (2 -> [20 x L] -> 1): warp-level mma.sync, each operand split into THREE BF16 terms
                              (an exact 24-bit split), the six cross terms of order <= 2, FP32 accumulate: FP32-equivalent
                              products with the activations chained from layer to layer in registers.  PINN_PREC_BF16X3 at
                              width 20 selects the same kernel with two terms (three MMAs). */
+    PINN_PREC_FP16X3 = 4  /* width 20: the same kernel with each operand split into TWO FP16 terms (22 significand bits, three
+                             MMAs) after an exact per-warp, per-channel power-of-two scaling into the FP16 range: near-FP32
+                             products at the cost of BF16X3. */
 } pinn_precision;
 
 /* Point sets of one training batch. */

@@ -17,7 +17,7 @@ xs = [O.sample(ocfg, k) for k in range(3)]
 w = O.init_params(ocfg).astype(np.float32)
 g_ref, s_ref = O.loss_grad(ocfg, w.astype(np.float64), *xs)
 l_ref = O.loss_from_sums(ocfg, s_ref)[0]
-for prec in (0, 1, 3):
+for prec in (0, 1, 3, 4):
     with P.Network(pcfg(precision=prec)) as net:
         out = net.loss_grad(); g = net.get_grads()
         err = np.abs(g - g_ref).max() / np.abs(g_ref).max()
@@ -35,7 +35,7 @@ w0 = O.init_params(ocfg).astype(np.float32)
 p_ref, _, _, l_ref, _ = O.train(ocfg, w0.astype(np.float64), 100, dtype=np.float64)
 p32, _, _, l32, _ = O.train(ocfg, w0, 100, dtype=np.float32)
 print(f"cpu f32 oracle: loss30={np.abs(l32[:30,0]/l_ref[:30,0]-1).max():.2e} loss100={np.abs(l32[:,0]/l_ref[:,0]-1).max():.2e} params={np.abs(p32-p_ref).max():.2e}")
-for prec in (0, 1, 3):
+for prec in (0, 1, 3, 4):
     with P.Network(pcfg(precision=prec)) as net:
         losses = np.array([net.train_step()["loss"] for _ in range(100)])
         w = net.get_params()
