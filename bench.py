@@ -89,6 +89,55 @@ def peaks():
     return p
 
 
+class NvmlSampler:
+    """SM clock + clock-event reasons through NVML (pynvml), polled every ~0.5 ms on a thread: the timed region of the small
+    configs lasts a few milliseconds, which `nvidia-smi -lms 100` cannot sample.  Same quantities as the recipe's line."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        self.h = None
+        try:
+            import torch
+            pr = torch.cuda.get_device_properties(index)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        self.sm, self.bits, self.stop_flag = [], 0, False
+        self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+
+    def start(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.0005)
+
+    def stop(self):
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        reasons = sorted(nm for bit, nm in self.REASONS.items() if self.bits & bit)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx, "samples": len(self.sm),
+                "reasons": reasons, "source": "nvml"}
+
+
+def make_sampler(index):
+    try:
+        return NvmlSampler(index)
+    except Exception:
+        return ClockSampler(index)
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -315,7 +364,7 @@ def main():
         net.train_step(read_loss=False)
     barrier()
     net.profile_get(reset=True)
-    sampler = ClockSampler(local_rank); sampler.start()
+    sampler = make_sampler(local_rank); sampler.start()
     t_wall0 = time.perf_counter()
     ms_total = timed_steps(args.steps, lambda: net.train_step(read_loss=False))
     barrier()

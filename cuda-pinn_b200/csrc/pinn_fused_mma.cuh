@@ -44,6 +44,7 @@ struct MmaArgs {
     float* stash;               // [rows][stash_per_row]
     int row0;
     long long stash_per_row;    // floats
+    float* x_copy;              // non-null: set.x is mapped HOST memory; interior tiles also store their points here (HBM)
 };
 
 constexpr int kMmaWarps = 4;                      // warps per CTA
@@ -296,6 +297,12 @@ __device__ __forceinline__ void mma_tile(const NetDims& nd, const MmaArgs& args,
         valid[h] = p < ps.n;
         #pragma unroll
         for (int k = 0; k < 3; k++) x[h][k] = (k < DIN && valid[h]) ? __ldg(ps.x + p * DIN + k) : 0.0f;
+        if constexpr (!VAL) {
+            if (args.x_copy != nullptr && t == 0 && valid[h]) {
+                #pragma unroll
+                for (int k = 0; k < DIN; k++) args.x_copy[p * DIN + k] = x[h][k];
+            }
+        }
     }
 
     // ------------------------------ forward ------------------------------

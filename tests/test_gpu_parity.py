@@ -371,3 +371,32 @@ def test_bf16x6_and_fp16x3_are_width_20_only(P, oracle):
         with pytest.raises(P.PinnError) as ei:
             P.Network(pcfg(P, oracle.make_config(oracle.PDE_HELMHOLTZ, 20, 4, 64, 64, 0), precision=prec))
         assert ei.value.code == 7
+
+
+def test_train_step_host_zero_copy_matches_the_copy_path(P, oracle):
+    """pinn_train_step_host with PINNED caller memory on the mma path reads the points over PCIe inside the kernel (no copy
+    operation) and polls the mapped loss record; with pageable memory it copies.  Both must equal set_points + train_step
+    bit for bit, and the resident HBM copy of the points must be the caller's afterwards."""
+    import torch
+    ocfg = oracle.baseline_config(2, n_interior=4099)
+    rng = np.random.default_rng(11)
+    steps = [np.stack([rng.uniform(-1, 1, 4099), rng.uniform(0, 1, 4099)], axis=1).astype(np.float32) for _ in range(3)]
+    pinned = torch.empty((4099, 2), dtype=torch.float32).pin_memory()
+    res = {}
+    for mode in ("pinned", "pageable", "set_points"):
+        with P.Network(pcfg(P, ocfg, precision=4)) as net:
+            out = []
+            for x in steps:
+                if mode == "pinned":
+                    pinned.copy_(torch.from_numpy(x))
+                    out.append(net.train_step_host(pinned.data_ptr(), len(x)))
+                elif mode == "pageable":
+                    out.append(net.train_step_host(x.copy(), len(x)))
+                else:
+                    net.set_points(0, x)
+                    out.append(net.train_step())
+            assert np.array_equal(net.get_points(0), steps[-1])
+            res[mode] = ([o["loss"] for o in out], [o["step"] for o in out], net.get_params())
+    for mode in ("pinned", "pageable"):
+        assert res[mode][0] == res["set_points"][0] and res[mode][1] == [1, 2, 3]
+        assert np.array_equal(res[mode][2].view(np.uint32), res["set_points"][2].view(np.uint32))
