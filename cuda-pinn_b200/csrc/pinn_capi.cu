@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <memory>
 #include <string>
 #include <vector>
@@ -990,19 +991,22 @@ static int read_out(pinn_ctx* c, pinn_step_out* out) {
 }
 
 // Result of the latest TRAINING step without a copy or a stream synchronisation: the step tail wrote the loss record and,
-// last, the step number into the mapped pinned record (loss_record); poll that.  The stream is queried now and then so a
-// failed launch cannot hang the caller.
+// last, the step number into the mapped pinned record (loss_record); poll that for a bounded time (steps of the narrow
+// nets take < 0.1 ms), then fall back to a stream synchronisation so long steps and failed launches behave as usual.
 static int read_step(pinn_ctx* c, pinn_step_out* out) {
     if (!out) return PINN_OK;
     volatile unsigned int* w = reinterpret_cast<volatile unsigned int*>(c->h_pinned);
     const unsigned int want = (unsigned int)c->host_step;
-    unsigned spins = 0;
-    while (w[3] != want || w[6] != want) {                // both halves of the record carry this step's number
-        if ((++spins & 0x3fffu) == 0) {
-            const cudaError_t e = cudaStreamQuery(c->stream);
-            if (e == cudaSuccess) { if (w[3] == want && w[6] == want) break; return read_out(c, out); }   // (defensive) take the copy path
-            if (e != cudaErrorNotReady) return fail(c, PINN_ERR_CUDA, std::string("pinn_train_step: ") + cudaGetErrorString(e));
-        }
+    // short steps: poll (bounded, ~0.3 ms); long steps: block in the driver like any other caller, then read the record
+    bool ready = false;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spins = 0;; spins++) {
+        if (w[3] == want && w[6] == want) { ready = true; break; }   // both halves of the record carry this step's number
+        if ((spins & 63u) == 63u && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(300)) break;
+    }
+    if (!ready) {
+        CUDA_TRY(c, "pinn_train_step", cudaStreamSynchronize(c->stream));
+        if (!(w[3] == want && w[6] == want)) return read_out(c, out);                        // (defensive) take the copy path
     }
     std::atomic_thread_fence(std::memory_order_acquire);
     volatile float* h = c->h_pinned;
