@@ -89,74 +89,23 @@ def peaks():
     return p
 
 
-class NvmlSampler:
-    """SM clock + clock-event reasons through NVML (pynvml) on a thread, 1 ms apart at first and backing off to 100 ms: the
-    timed region of the small configs lasts a few milliseconds, which `nvidia-smi -lms 100` cannot sample.  Same quantities
-    as the recipe's line."""
-    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
-
-    def __init__(self, index):
-        import pynvml
-        self.nv = pynvml
-        pynvml.nvmlInit()
-        self.h = None
-        try:
-            import torch
-            pr = torch.cuda.get_device_properties(index)
-            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
-            self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
-        except Exception:
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        self.sm, self.bits, self.stop_flag = [], 0, False
-        self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-
-    def start(self):
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
-
-    def _run(self):
-        # 1 ms spacing at first (the narrow-net timed region lasts milliseconds), backing off to the recipe's 100 ms:
-        # sustained kHz-rate NVML queries stall a long, power-capped run (measured: C5 at full size never finished)
-        nv, gap = self.nv, 0.001
-        while not self.stop_flag:
-            try:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-            except Exception:
-                pass
-            time.sleep(gap)
-            gap = min(0.1, gap * 1.5)
-
-    def stop(self):
-        self.stop_flag = True
-        self.t.join(timeout=2)
-        reasons = sorted(nm for bit, nm in self.REASONS.items() if self.bits & bit)
-        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx, "samples": len(self.sm),
-                "reasons": reasons, "source": "nvml"}
-
-
-def make_sampler(index):
-    if os.environ.get("PINN_BENCH_SAMPLER") == "smi":
-        return ClockSampler(index)
-    try:
-        return NvmlSampler(index)
-    except Exception:
-        return ClockSampler(index)
-
-
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe), as a SUBPROCESS polling every
+    20 ms (in-process NVML polling from a thread stalled long power-capped runs: C5 at full size never finished).  It is
+    started before the warm-up (nvidia-smi needs ~0.2 s to produce its first row); rows are stamped on arrival and only
+    those inside the load window [mark_begin, mark_end] are used."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_begin, self.t_end = None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -165,7 +114,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -177,7 +132,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        lo = self.t_begin if self.t_begin is not None else 0.0
+        hi = (self.t_end if self.t_end is not None else float("inf")) + 0.02      # a row describes the 20 ms before it
+        for ts, r in self.rows:
+            if not (lo <= ts <= hi):
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for nm, v in zip(names, r[3:7]):
@@ -366,17 +325,31 @@ def main():
         return sum(a.elapsed_time(b) for a, b in evs)
 
     # ---- device-resident throughput (CUDA-graph step replay) ----
+    sampler = ClockSampler(local_rank); sampler.start()
     for _ in range(args.warmup):
         net.train_step(read_loss=False)
     barrier()
     net.profile_get(reset=True)
-    sampler = make_sampler(local_rank); sampler.start()
+    sampler.mark_begin()
     t_wall0 = time.perf_counter()
     ms_total = timed_steps(args.steps, lambda: net.train_step(read_loss=False))
     barrier()
     wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
     launches = net.profile_get(reset=True)["launches"]
+    # the narrow-net timed region lasts milliseconds, below nvidia-smi's 20 ms period: keep the SAME load (identical untimed
+    # steps, L2 flushed) running until the clock samples cover about 0.3 s that contains the timed region.  The step count
+    # comes from the max-over-ranks step time, so every rank runs the same number of (collective) steps.
+    tl = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+    est_step_s = float(tl.item()) / args.steps * 1e-3 + 1.0e-4          # + the L2 flush memset
+    load_steps = max(0, min(5000, int(0.3 / est_step_s) - args.steps))
+    if load_steps:
+        timed_steps(load_steps, lambda: net.train_step(read_loss=False))
+    sampler.mark_end()
+    clocks = sampler.stop()
+    clocks["window"] = f"timed region + {load_steps} identical untimed steps (about 0.3 s under the same load)" if load_steps else "timed region"
+    net.profile_get(reset=True)
     # ---- per-kernel CUDA-event pass for the roofline (same steps, direct launches bracketed by events) ----
     net.profile_enable(True)
     timed_steps(min(args.steps, 10), lambda: net.train_step(read_loss=False))
