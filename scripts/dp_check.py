@@ -18,7 +18,9 @@ which = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4099
 K = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 nb = 257
-cfg = P.default_config(which, n_interior=n, n_boundary=nb, n_initial=0 if which == 3 else nb, rank=rank, nranks=world, device=local)
+prec = int(os.environ.get("PINN_DP_PRECISION", "0"))      # pinn_precision (4 = FP16X3 on the width-20 mma kernel)
+cfg = P.default_config(which, n_interior=n, n_boundary=nb, n_initial=0 if which == 3 else nb, rank=rank, nranks=world, device=local,
+                       precision=prec)
 net = P.Network(cfg)
 box = [P.Network.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(box, src=0)
@@ -50,7 +52,7 @@ if rank == 0:
     dl = float(np.abs(np.array(losses + [o["loss"]]) / l_ref[:, 0] - 1).max())
     dp = float(np.abs(net.get_params() - p_ref).max())
     good = ok and dl < 1e-5 and dp < 1e-5
-    print(f"DP_CHECK {'OK' if good else 'FAIL'} ranks={world} collective={'p2p-fused' if p2p else 'nccl'} identical_across_ranks={ok} loss_rel={dl:.2e} params_abs={dp:.2e}", flush=True)
+    print(f"DP_CHECK {'OK' if good else 'FAIL'} ranks={world} collective={'p2p-fused' if p2p else 'nccl'} precision={prec} identical_across_ranks={ok} loss_rel={dl:.2e} params_abs={dp:.2e}", flush=True)
     if not good:
         sys.exit(1)
 net.close()
