@@ -162,51 +162,57 @@ __global__ void adam_kernel(const NetDims nd, const AdamArgs a, float* __restric
     adam_one(nd, a, params, paramsT, m, v, gbuf[i], (double)(*step), i, fm);
 }
 
-// Single-GPU step tail in ONE launch: fixed-order sum of the partial rows (as reduce_partials_kernel), Adam on the
-// block's own 32 columns, mirrors; the last block to finish records the loss and bumps the step counter.
-__global__ void __launch_bounds__(1024)
+// Single-GPU step tail in ONE launch: fixed-order sum of the partial rows, Adam on the block's own 32 columns, mirrors; the
+// last block to finish records the loss and bumps the step counter.  Latency-oriented shape (the step is ~80 us, this kernel
+// must not be 15 of them): block = 8 column quads x 128 row lanes, float4 loads, so a thread walks rows/128 rows (13 for the
+// 1,700 warp rows of C2) with 4 loads in flight; lane sums meet in shared memory and are added in lane order (deterministic).
+constexpr int kTailLanes = 128;
+__global__ void __launch_bounds__(8 * kTailLanes)
 reduce_adam_kernel(const NetDims nd, const AdamArgs a, float* __restrict__ part_a, int rows_a, int zero_a,
                    float* __restrict__ part_b, int rows_b, float* __restrict__ params, float* __restrict__ paramsT,
                    float* __restrict__ m, float* __restrict__ v, float* __restrict__ gbuf, unsigned long long* __restrict__ step,
                    float* __restrict__ loss_out, int* __restrict__ flag, unsigned int* __restrict__ done_counter, const FragMirror fm,
                    float* hrec) {
-    __shared__ float part[32][33];
-    constexpr int RU = 8;
+    __shared__ float part[kTailLanes][33];
+    constexpr int RU = 4;
     const int PP = nd.PP, n_out = nd.P + 3;
-    const int col = blockIdx.x * 32 + threadIdx.x;
+    const int col0 = blockIdx.x * 32 + threadIdx.x * 4;    // this thread's column quad (PP is a multiple of 32: always inside a row)
     const unsigned long long tstep = *step + 1ULL;         // every block reads it before the LAST block writes it back
-    float s = 0.0f;
-    if (col < n_out) {
-        auto sum_rows = [&](const float* __restrict__ base, int rows) {
-            for (int r0 = threadIdx.y; r0 < rows; r0 += 32 * RU) {
-                float vv[RU];
-                #pragma unroll
-                for (int u = 0; u < RU; u++) {
-                    const int r = r0 + 32 * u;
-                    vv[u] = (r < rows) ? __ldcg(base + (size_t)r * PP + col) : 0.0f;
-                }
-                #pragma unroll
-                for (int u = 0; u < RU; u++) s += vv[u];
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto sum_rows = [&](float* __restrict__ base, int rows, bool zero) {
+        for (int r0 = threadIdx.y; r0 < rows; r0 += kTailLanes * RU) {
+            float4 vv[RU];
+            #pragma unroll
+            for (int u = 0; u < RU; u++) {
+                const int r = r0 + kTailLanes * u;
+                vv[u] = (r < rows) ? __ldcg(reinterpret_cast<const float4*>(base + (size_t)r * PP + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        };
-        sum_rows(part_a, rows_a);
-        sum_rows(part_b, rows_b);
-        if (zero_a) {                                     // (rows written by plain stores — the mma path — need none)
-            for (int r = threadIdx.y; r < rows_a; r += 32) part_a[(size_t)r * PP + col] = 0.0f;
-            for (int r = threadIdx.y; r < rows_b; r += 32) part_b[(size_t)r * PP + col] = 0.0f;
+            #pragma unroll
+            for (int u = 0; u < RU; u++) {                 // rows in increasing order: fixed summation order
+                s.x += vv[u].x; s.y += vv[u].y; s.z += vv[u].z; s.w += vv[u].w;
+                const int r = r0 + kTailLanes * u;
+                if (zero && r < rows) *reinterpret_cast<float4*>(base + (size_t)r * PP + col0) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    };
+    sum_rows(part_a, rows_a, zero_a != 0);
+    sum_rows(part_b, rows_b, zero_a != 0);
+    part[threadIdx.y][threadIdx.x * 4 + 0] = s.x; part[threadIdx.y][threadIdx.x * 4 + 1] = s.y;
+    part[threadIdx.y][threadIdx.x * 4 + 2] = s.z; part[threadIdx.y][threadIdx.x * 4 + 3] = s.w;
+    __syncthreads();
+    const int tid = threadIdx.y * 8 + threadIdx.x;
+    if (tid < 32) {
+        const int col = blockIdx.x * 32 + tid;
+        if (col < n_out) {
+            float t = 0.0f;
+            #pragma unroll 16
+            for (int y = 0; y < kTailLanes; y++) t += part[y][tid];
+            gbuf[col] = t;
+            if (col < nd.P) adam_one(nd, a, params, paramsT, m, v, t, (double)tstep, col, fm);
         }
     }
-    part[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
-    if (threadIdx.y == 0 && col < n_out) {
-        float t = 0.0f;
-        #pragma unroll
-        for (int y = 0; y < 32; y++) t += part[y][threadIdx.x];
-        gbuf[col] = t;
-        if (col < nd.P) adam_one(nd, a, params, paramsT, m, v, t, (double)tstep, col, fm);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
+    if (tid == 0) {
         __threadfence();
         if (atomicAdd(done_counter, 1u) == gridDim.x - 1) {
             *done_counter = 0u;
@@ -846,7 +852,7 @@ static FragMirror frag_mirror(const pinn_ctx* c) {
 // Single-GPU tail of the step: reduce + Adam + mirrors + loss record in one launch.
 static int run_tail(pinn_ctx* c) {
     const int n_out = c->nd.P + 3;
-    reduce_adam_kernel<<<(n_out + 31) / 32, dim3(32, 32), 0, c->stream>>>(
+    reduce_adam_kernel<<<(n_out + 31) / 32, dim3(8, kTailLanes), 0, c->stream>>>(
         c->nd, c->adam, c->d_partial, c->rows_a, c->kern_mma ? 0 : 1, c->d_partial + (size_t)c->rows_cap_a * c->nd.PP, c->rows_b,
         c->d_params, c->d_paramsT, c->d_m, c->d_v, c->d_gbuf, c->d_step, c->d_loss, c->d_flag, c->d_tail, frag_mirror(c), c->d_hrec);
     c->step_launches++;
