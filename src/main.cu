@@ -3,8 +3,8 @@
 // tensor<T> API plus network<T> (include/network.cuh): the loop, the loss log, checkpoint / resume and
 // the accuracy check live here; every step runs on the GPU inside libpinn_b200.so.
 //
-//   pinn_train [--config 1..5] [--points N] [--width H --depth L] [--steps N] [--log-every K]
-//              [--resample-every K] [--csv file] [--save file] [--resume file] [--eval nodes_per_axis]
+//   pinn_train [--config 1..5] [--points N] [--width H --depth L] [--precision fp32|fp16x3|bf16x6|bf16x3|bf16] [--steps N]
+//              [--log-every K] [--resample-every K] [--csv file] [--save file] [--resume file] [--eval nodes_per_axis]
 //
 // Built into bin/pinn_train by the repo's Makefile next to the drop-in test (it needs the reference's
 // tensor headers, which exist only where the reference checkout is mounted; the binary travels).
@@ -26,13 +26,14 @@ namespace {
         int config = 2;
         size_t points = 0, steps = 1000, log_every = 100, resample_every = 0, eval = 0;
         int width = 0, depth = 0;
-        std::string csv, save, resume;
+        std::string csv, save, resume, precision;
     };
 
     [[noreturn]] void usage(const std::string &why) {
         std::cerr << "pinn_train: " << why << "\n"
-                  << "usage: pinn_train [--config 1..5] [--points N] [--width H --depth L] [--steps N] [--log-every K]\n"
-                  << "                  [--resample-every K] [--csv file] [--save file] [--resume file] [--eval nodes_per_axis]" << endl;
+                  << "usage: pinn_train [--config 1..5] [--points N] [--width H --depth L] [--precision fp32|fp16x3|bf16x6|bf16x3|bf16]\n"
+                  << "                  [--steps N] [--log-every K] [--resample-every K] [--csv file] [--save file] [--resume file]\n"
+                  << "                  [--eval nodes_per_axis]" << endl;
         std::exit(2);
     }
 
@@ -67,7 +68,7 @@ namespace {
         o.log_every = number("log-every", 100);
         o.resample_every = number("resample-every", 0);
         o.eval = number("eval", 0);
-        o.csv = text("csv"); o.save = text("save"); o.resume = text("resume");
+        o.csv = text("csv"); o.save = text("save"); o.resume = text("resume"); o.precision = text("precision");
         if (!kv.empty()) usage("unknown option --" + kv.begin()->first);
         if (o.log_every == 0) usage("--log-every must be positive");
         return o;
@@ -85,6 +86,13 @@ int main(int argc, char **argv) {
         }
         if (opt.width) cfg.width = opt.width;
         if (opt.depth) cfg.depth = opt.depth;
+        if (!opt.precision.empty()) {
+            static const std::map<std::string, int> known = {{"fp32", PINN_PREC_FP32}, {"fp16x3", PINN_PREC_FP16X3}, {"bf16x6", PINN_PREC_BF16X6},
+                                                             {"bf16x3", PINN_PREC_BF16X3}, {"bf16", PINN_PREC_BF16}};
+            const auto it = known.find(opt.precision);
+            if (it == known.end()) usage("--precision must be one of fp32, fp16x3, bf16x6, bf16x3, bf16");
+            cfg.precision = it->second;
+        }
 
         network_f net(cfg);
         net.sample();

@@ -172,6 +172,22 @@ def test_training_driver_logs_checkpoints_resumes_and_matches_the_library(P, ora
 
 
 @pytest.mark.skipif(not os.path.exists(TRAIN), reason="bin/pinn_train is built only where the reference headers are present")
+def test_training_driver_precision_option_selects_the_mma_kernel(P, tmp_path):
+    log = str(tmp_path / "loss.csv")
+    r = subprocess.run([TRAIN, "--config", "1", "--precision", "fp16x3", "--steps", "40", "--log-every", "20", "--csv", log],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = list(csv.DictReader(open(log)))
+    with P.Network(P.default_config(1, precision=P.PREC_FP16X3)) as net:
+        want = [net.train_steps(20) for _ in range(2)]
+        assert net.profile_get()["kernel_id"] == 204
+    for row, w in zip(rows, want):
+        assert np.float32(row["loss"]) == np.float32(w["loss"])
+    r = subprocess.run([TRAIN, "--precision", "fp8"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "--precision must be one of" in r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(TRAIN), reason="bin/pinn_train is built only where the reference headers are present")
 def test_training_driver_rejects_bad_arguments():
     for args in (["--steps"], ["--bogus", "1"], ["--steps", "abc"], ["steps", "3"], ["--log-every", "0"]):
         r = subprocess.run([TRAIN] + args, capture_output=True, text=True, timeout=60)
