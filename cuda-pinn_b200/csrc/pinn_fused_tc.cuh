@@ -333,6 +333,10 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                     umma::mma_commit(&mma_bar);
                 }
                 wait_mma();
+                // width 256 runs two halves per layer: without a block barrier here thread 0 could commit the second half
+                // before a delayed warp has polled the first — mma_bar would then be TWO phases ahead of that warp, which
+                // sees its old parity again and waits forever (rare: observed as a hang only at C5's full 8.4 M points)
+                if (nhalf > 1) __syncthreads();
                 if (tid == 0) {                           // prefetch the next weights under the epilogue
                     if (h + 1 < nhalf) w_request(l, h + 1);
                     else if (l < L) w_request(l + 1, 0);
@@ -634,6 +638,7 @@ fused_step_tc(const NetDims nd, const TcArgs ta) {
                         umma::mma_commit(&mma_bar);
                     }
                     wait_mma();
+                    if (nhalf > 1) __syncthreads();       // (same two-commit hazard as in the forward loop)
                     if (tid == 0) {
                         if (h + 1 < nhalf) w_request(l, h + 1);
                         else if (l > 2) w_request(l - 1, 0);
