@@ -137,3 +137,15 @@ def test_training_driver_argument_errors_without_a_gpu():
     if not torch.cuda.is_available():          # no CPU fallback: the driver reports the library's error and exits 1
         r = subprocess.run([exe, "--config", "1", "--steps", "1"], capture_output=True, text=True, timeout=120)
         assert r.returncode == 1 and "pinn_train: " in r.stderr
+
+
+def test_python_binding_enums_match_the_header(P):
+    """pinn_precision / pinn_pde / pinn_point_set values of include/pinn_abi.h against the ctypes binding's constants."""
+    src = open(os.path.join(ROOT, "include", "pinn_abi.h")).read()
+    vals = {k: int(v) for k, v in re.findall(r"\b(PINN_(?:PREC|PDE|SET)_[A-Z0-9_]+)\s*=\s*(\d+)", src)}
+    assert vals["PINN_PREC_FP32"] == P.PREC_FP32 and vals["PINN_PREC_BF16X3"] == P.PREC_BF16X3 and vals["PINN_PREC_BF16"] == P.PREC_BF16
+    assert vals["PINN_PREC_BF16X6"] == P.PREC_BF16X6 and vals["PINN_PREC_FP16X3"] == P.PREC_FP16X3
+    assert [vals[k] for k in ("PINN_PDE_BURGERS", "PINN_PDE_HELMHOLTZ", "PINN_PDE_ALLEN_CAHN", "PINN_PDE_NAVIER_STOKES", "PINN_PDE_HEAT")] == \
+        [P.PDE_BURGERS, P.PDE_HELMHOLTZ, P.PDE_ALLEN_CAHN, P.PDE_NAVIER_STOKES, P.PDE_HEAT]
+    assert [vals[k] for k in ("PINN_SET_INTERIOR", "PINN_SET_BOUNDARY", "PINN_SET_INITIAL")] == [P.SET_INTERIOR, P.SET_BOUNDARY, P.SET_INITIAL]
+    assert sorted(v for k, v in vals.items() if k.startswith("PINN_PREC_")) == [0, 1, 2, 3, 4]
