@@ -109,11 +109,9 @@ __device__ __forceinline__ void frag_mirror_store(const FragMirror& fm, int l, i
 
 // Adam for parameter i + refresh of the transposed mirror W^T[l] ([fan_out, fan_in]) and, where the
 // handle has one, of the BF16 fragment mirror.
-__device__ __forceinline__ void adam_one(const NetDims& nd, const AdamArgs& a, float* __restrict__ params,
-                                         float* __restrict__ paramsT, float* __restrict__ m, float* __restrict__ v,
-                                         float g, double t, int i, const FragMirror& fm) {
-    const float c1 = (float)(1.0 / (1.0 - pow((double)a.beta1, t)));
-    const float c2 = (float)(1.0 / (1.0 - pow((double)a.beta2, t)));
+__device__ __forceinline__ void adam_core(const NetDims& nd, const AdamArgs& a, float* __restrict__ params,
+                                          float* __restrict__ paramsT, float* __restrict__ m, float* __restrict__ v,
+                                          float g, float c1, float c2, int i, const FragMirror& fm) {
     const float mi = a.beta1 * m[i] + (1.0f - a.beta1) * g;
     const float vi = a.beta2 * v[i] + (1.0f - a.beta2) * (g * g);
     m[i] = mi; v[i] = vi;
@@ -130,6 +128,13 @@ __device__ __forceinline__ void adam_one(const NetDims& nd, const AdamArgs& a, f
     } else {
         paramsT[i] = w;
     }
+}
+__device__ __forceinline__ void adam_one(const NetDims& nd, const AdamArgs& a, float* __restrict__ params,
+                                         float* __restrict__ paramsT, float* __restrict__ m, float* __restrict__ v,
+                                         float g, double t, int i, const FragMirror& fm) {
+    const float c1 = (float)(1.0 / (1.0 - pow((double)a.beta1, t)));
+    const float c2 = (float)(1.0 / (1.0 - pow((double)a.beta2, t)));
+    adam_core(nd, a, params, paramsT, m, v, g, c1, c2, i, fm);
 }
 
 // hrec (may be null): the handle's MAPPED pinned host record, two 16-byte halves {loss, mse_r, mse_b, seq} {mse_0, flag, seq, 0}
@@ -155,9 +160,11 @@ __device__ __forceinline__ void loss_record(const NetDims& nd, const AdamArgs& a
 __global__ void adam_kernel(const NetDims nd, const AdamArgs a, float* __restrict__ params,
                             float* __restrict__ paramsT, float* __restrict__ m, float* __restrict__ v,
                             const float* __restrict__ gbuf, const unsigned long long* __restrict__ step,
-                            float* __restrict__ loss_out, int* __restrict__ flag, int apply, const FragMirror fm, float* hrec) {
+                            float* __restrict__ loss_out, int* __restrict__ flag, int apply, const FragMirror fm, float* hrec,
+                            double* __restrict__ beta_pow) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) loss_record(nd, a, gbuf[nd.P + 0], gbuf[nd.P + 1], gbuf[nd.P + 2], loss_out, flag, apply ? hrec : nullptr, *step);
+    if (i == 0 && apply) { beta_pow[0] *= (double)a.beta1; beta_pow[1] *= (double)a.beta2; }   // keep the single-GPU tail's running powers in step
     if (i >= nd.P || !apply) return;
     adam_one(nd, a, params, paramsT, m, v, gbuf[i], (double)(*step), i, fm);
 }
@@ -172,12 +179,15 @@ reduce_adam_kernel(const NetDims nd, const AdamArgs a, float* __restrict__ part_
                    float* __restrict__ part_b, int rows_b, float* __restrict__ params, float* __restrict__ paramsT,
                    float* __restrict__ m, float* __restrict__ v, float* __restrict__ gbuf, unsigned long long* __restrict__ step,
                    float* __restrict__ loss_out, int* __restrict__ flag, unsigned int* __restrict__ done_counter, const FragMirror fm,
-                   float* hrec) {
+                   float* hrec, double* __restrict__ beta_pow) {
     __shared__ float part[kTailLanes][33];
     constexpr int RU = 4;
     const int PP = nd.PP, n_out = nd.P + 3;
     const int col0 = blockIdx.x * 32 + threadIdx.x * 4;    // this thread's column quad (PP is a multiple of 32: always inside a row)
     const unsigned long long tstep = *step + 1ULL;         // every block reads it before the LAST block writes it back
+    // bias corrections from the running powers beta^t (one multiply per step instead of two double pow() in the only warp
+    // of the block that runs Adam — they were the longest dependent chain of this kernel)
+    const double b1t = beta_pow[0] * (double)a.beta1, b2t = beta_pow[1] * (double)a.beta2;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     auto sum_rows = [&](float* __restrict__ base, int rows, bool zero) {
         for (int r0 = threadIdx.y; r0 < rows; r0 += kTailLanes * RU) {
@@ -208,7 +218,7 @@ reduce_adam_kernel(const NetDims nd, const AdamArgs a, float* __restrict__ part_
             #pragma unroll 16
             for (int y = 0; y < kTailLanes; y++) t += part[y][tid];
             gbuf[col] = t;
-            if (col < nd.P) adam_one(nd, a, params, paramsT, m, v, t, (double)tstep, col, fm);
+            if (col < nd.P) adam_core(nd, a, params, paramsT, m, v, t, (float)(1.0 / (1.0 - b1t)), (float)(1.0 / (1.0 - b2t)), col, fm);
         }
     }
     __syncthreads();
@@ -218,6 +228,7 @@ reduce_adam_kernel(const NetDims nd, const AdamArgs a, float* __restrict__ part_
             *done_counter = 0u;
             __threadfence();
             *step = tstep;
+            beta_pow[0] = b1t; beta_pow[1] = b2t;
             loss_record(nd, a, __ldcg(gbuf + nd.P), __ldcg(gbuf + nd.P + 1), __ldcg(gbuf + nd.P + 2), loss_out, flag, hrec, tstep);
         }
     }
@@ -263,7 +274,8 @@ reduce_exchange_adam_kernel(const NetDims nd, const AdamArgs a, float* __restric
                             float* __restrict__ part_b, int rows_b, float* __restrict__ params,
                             float* __restrict__ paramsT, float* __restrict__ m, float* __restrict__ v,
                             float* __restrict__ gbuf, unsigned long long* __restrict__ step, unsigned long long tstep,
-                            float* __restrict__ loss_out, int* __restrict__ flag, const P2PArgs x, const FragMirror fm, float* hrec) {
+                            float* __restrict__ loss_out, int* __restrict__ flag, const P2PArgs x, const FragMirror fm, float* hrec,
+                            double* __restrict__ beta_pow) {
     __shared__ float part[32][33];
     constexpr int RU = 8;
     const int PP = nd.PP, n_out = nd.P + 3;
@@ -334,6 +346,7 @@ reduce_exchange_adam_kernel(const NetDims nd, const AdamArgs a, float* __restric
                 s3[q] = t;
             }
             loss_record(nd, a, s3[0], s3[1], s3[2], loss_out, flag, hrec, tstep);
+            beta_pow[0] *= (double)a.beta1; beta_pow[1] *= (double)a.beta2;
         }
     }
 }
@@ -442,6 +455,7 @@ struct pinn_ctx {
     float* d_xchg = nullptr; float* peer_ptr[kMaxP2PRanks] = {nullptr}; bool p2p_ready = false;
     unsigned long long xseq = 0; unsigned int* d_done = nullptr;
     unsigned int* d_tail = nullptr;     // arrival counter of reduce_adam_kernel
+    double* d_beta_pow = nullptr;       // {beta1^t, beta2^t} at the device step count t (single-GPU tail only)
     std::string err;
     // profiling
     bool prof = false;
@@ -713,6 +727,17 @@ static int configure_kernels(pinn_ctx* c) {
     return PINN_OK;
 }
 
+// {beta1^t, beta2^t} as the ITERATED product the tail kernel forms (bit-identical, so a resumed run matches an uninterrupted one)
+static int upload_beta_pow(pinn_ctx* c, uint64_t t) {
+    double p[2] = {1.0, 1.0};
+    const double b1 = (double)c->cfg.beta1, b2 = (double)c->cfg.beta2;
+    for (uint64_t k = 0; k < t; k++) { p[0] *= b1; p[1] *= b2; }
+    if (cudaMemcpyAsync(c->d_beta_pow, p, sizeof(p), cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess)
+        return fail(c, PINN_ERR_CUDA, "pinn_set_optimizer: upload of the Adam bias powers failed");
+    return PINN_OK;
+}
+
 static int tiles_of(uint64_t n, int tp) { return (int)((n + tp - 1) / tp); }
 
 static void host_init_params(const NetDims& nd, uint64_t seed, std::vector<float>& w) {
@@ -854,7 +879,8 @@ static int run_tail(pinn_ctx* c) {
     const int n_out = c->nd.P + 3;
     reduce_adam_kernel<<<(n_out + 31) / 32, dim3(8, kTailLanes), 0, c->stream>>>(
         c->nd, c->adam, c->d_partial, c->rows_a, c->kern_mma ? 0 : 1, c->d_partial + (size_t)c->rows_cap_a * c->nd.PP, c->rows_b,
-        c->d_params, c->d_paramsT, c->d_m, c->d_v, c->d_gbuf, c->d_step, c->d_loss, c->d_flag, c->d_tail, frag_mirror(c), c->d_hrec);
+        c->d_params, c->d_paramsT, c->d_m, c->d_v, c->d_gbuf, c->d_step, c->d_loss, c->d_flag, c->d_tail, frag_mirror(c), c->d_hrec,
+        c->d_beta_pow);
     c->step_launches++;
     refresh_wq(c, true);
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
@@ -871,7 +897,7 @@ static int run_exchange_apply(pinn_ctx* c) {
     reduce_exchange_adam_kernel<<<(n_out + 31) / 32, dim3(32, 32), 0, c->stream>>>(
         c->nd, c->adam, c->d_partial, c->rows_a, c->d_partial + (size_t)c->rows_cap_a * c->nd.PP, c->rows_b,
         c->d_params, c->d_paramsT, c->d_m, c->d_v, c->d_gbuf, c->d_step, (unsigned long long)(c->host_step + 1),
-        c->d_loss, c->d_flag, x, frag_mirror(c), c->d_hrec);
+        c->d_loss, c->d_flag, x, frag_mirror(c), c->d_hrec, c->d_beta_pow);
     c->step_launches++;
     refresh_wq(c, true);
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
@@ -900,7 +926,8 @@ static int run_allreduce(pinn_ctx* c) {
 
 static int run_apply(pinn_ctx* c, int apply) {
     adam_kernel<<<(c->nd.P + 255) / 256, 256, 0, c->stream>>>(c->nd, c->adam, c->d_params, c->d_paramsT, c->d_m, c->d_v,
-                                                            c->d_gbuf, c->d_step, c->d_loss, c->d_flag, apply, frag_mirror(c), c->d_hrec);
+                                                            c->d_gbuf, c->d_step, c->d_loss, c->d_flag, apply, frag_mirror(c), c->d_hrec,
+                                                            c->d_beta_pow);
     c->step_launches++;
     if (apply) refresh_wq(c, true);
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
@@ -1114,6 +1141,7 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     TRY_C(cudaMalloc(&c->d_loss, 8 * sizeof(float)));          // [0..3] loss record, [4] overflow flag word: one D2H copy per read-back
     TRY_C(cudaMalloc(&c->d_step, sizeof(unsigned long long)));
     TRY_C(cudaMalloc(&c->d_tail, sizeof(unsigned int)));
+    TRY_C(cudaMalloc(&c->d_beta_pow, 2 * sizeof(double)));
     TRY_C(cudaMemsetAsync(c->d_tail, 0, sizeof(unsigned int), c->stream));
     c->d_flag = reinterpret_cast<int*>(c->d_loss + 4);
     TRY_C(cudaHostAlloc(&c->h_pinned, 16 * sizeof(float), cudaHostAllocMapped));
@@ -1149,7 +1177,7 @@ void pinn_destroy(pinn_ctx* c) {
     cudaFree(c->d_step); cudaFree(c->d_wq); cudaFree(c->d_ring); cudaFree(c->d_wfrag);
     for (int r = 0; r < kMaxP2PRanks; r++)
         if (c->peer_ptr[r] && c->peer_ptr[r] != c->d_xchg) cudaIpcCloseMemHandle(c->peer_ptr[r]);
-    cudaFree(c->d_xchg); cudaFree(c->d_done); cudaFree(c->d_tail);
+    cudaFree(c->d_xchg); cudaFree(c->d_done); cudaFree(c->d_tail); cudaFree(c->d_beta_pow);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     drop_graph(c);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -1175,6 +1203,7 @@ int pinn_set_params(pinn_ctx* c, const float* flat, size_t n, int reset_optimize
     }
     CUDA_TRY(c, "pinn_set_params", cudaStreamSynchronize(c->stream));
     if (reset_optimizer && c->h_pinned) { c->h_pinned[3] = 0.0f; c->h_pinned[6] = 0.0f; }         // sequence words of read_step
+    if (reset_optimizer) { const int rb = upload_beta_pow(c, 0); if (rb) return rb; }
     return PINN_OK;
 }
 
@@ -1209,6 +1238,7 @@ int pinn_set_optimizer(pinn_ctx* c, const float* m, const float* v, size_t n, ui
     CUDA_TRY(c, "pinn_set_optimizer", cudaStreamSynchronize(c->stream));
     c->host_step = step;
     c->h_pinned[3] = 0.0f; c->h_pinned[6] = 0.0f;                                  // sequence words of read_step
+    { const int rb = upload_beta_pow(c, step); if (rb) return rb; }
     return PINN_OK;
 }
 
