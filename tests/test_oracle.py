@@ -149,3 +149,66 @@ def test_empty_and_tiny_sets(oracle):
     assert xf.shape == (1, 2) and x0.shape == (0, 2)
     g, s = oracle.loss_grad(cfg, oracle.init_params(cfg).astype(np.float64), xf, xb, x0)
     assert np.isfinite(g).all() and s[2] == 0
+
+
+@pytest.mark.parametrize("R", [2, 3])
+def test_shard_gradients_add_up_to_the_global_gradient(oracle, R):
+    """The data-parallel contract: seeds are scaled by 1/N_global, so the per-shard gradients and loss sums of
+    any partition ADD UP to the single-rank result."""
+    cfg = oracle.make_config(oracle.PDE_ALLEN_CAHN, 12, 3, 1001, 97, 103)
+    xs = [oracle.sample(cfg, k) for k in range(3)]
+    rng = np.random.default_rng(2)
+    p = (oracle.init_params(cfg) + 0.05 * rng.standard_normal(oracle.num_params(cfg))).astype(np.float64)
+    g_all, s_all = oracle.loss_grad(cfg, p, *xs)
+    g_sum, s_sum = np.zeros_like(g_all), np.zeros(3)
+    for r in range(R):
+        parts = []
+        for k in range(3):
+            b, e = oracle.shard_range(len(xs[k]), r, R)
+            parts.append(xs[k][b:e])
+        g, s = oracle.loss_grad(cfg, p, *parts)
+        g_sum += g; s_sum += s
+    assert rel_err(g_sum, g_all) < 1e-12 and rel_err(s_sum, s_all) < 1e-12
+
+
+def test_gradient_is_linear_in_the_loss_weights(oracle):
+    cfg = oracle.make_config(oracle.PDE_BURGERS, 20, 4, 512, 64, 64)
+    xs = [oracle.sample(cfg, k) for k in range(3)]
+    p = oracle.init_params(cfg).astype(np.float64)
+    parts = []
+    for lam in ((1, 0, 0), (0, 1, 0), (0, 0, 1)):
+        c = cfg.copy(); c.lambda_r, c.lambda_b, c.lambda_0 = lam
+        parts.append(oracle.loss_grad(c, p, *xs)[0])
+    c = cfg.copy(); c.lambda_r, c.lambda_b, c.lambda_0 = 0.25, 3.0, 7.5
+    g, _ = oracle.loss_grad(c, p, *xs)
+    assert rel_err(g, 0.25 * parts[0] + 3.0 * parts[1] + 7.5 * parts[2]) < 1e-12
+
+
+def test_closed_form_solutions_satisfy_their_pdes():
+    """The analytic solutions the product reports errors against (pinn_exact_solution; tests/test_abi_cpu.py pins the library
+    to these closed forms) really solve the PDEs of SURVEY.md Appendix B: residuals by central differences in float64."""
+    rng = np.random.default_rng(4)
+    h = 1e-4
+    d1 = lambda f, x, k: (f(*[xi + (h if i == k else 0) for i, xi in enumerate(x)]) - f(*[xi - (h if i == k else 0) for i, xi in enumerate(x)])) / (2 * h)
+    d2 = lambda f, x, k: (f(*[xi + (h if i == k else 0) for i, xi in enumerate(x)]) - 2 * f(*x) + f(*[xi - (h if i == k else 0) for i, xi in enumerate(x)])) / h ** 2
+    pi = np.pi
+    # Helmholtz, k = 1: u_xx + u_yy + k^2 u = q = (k^2 - pi^2 - 16 pi^2) u*
+    u = lambda x, y: np.sin(pi * x) * np.sin(4 * pi * y)
+    pt = (rng.uniform(-1, 1, 50), rng.uniform(-1, 1, 50))
+    r = d2(u, pt, 0) + d2(u, pt, 1) + u(*pt) - (1 - pi ** 2 - 16 * pi ** 2) * u(*pt)
+    assert np.abs(r).max() < 1e-4
+    # heat, alpha = 0.05: u_t = alpha (u_xx + u_yy)
+    alpha = 0.05
+    u = lambda x, y, t: np.sin(pi * x) * np.sin(pi * y) * np.exp(-2 * alpha * pi ** 2 * t)
+    pt = (rng.uniform(-1, 1, 50), rng.uniform(-1, 1, 50), rng.uniform(0.1, 0.9, 50))
+    assert np.abs(d1(u, pt, 2) - alpha * (d2(u, pt, 0) + d2(u, pt, 1))).max() < 1e-5
+    # Navier-Stokes, nu = 0.01: Taylor-Green vortex
+    nu = 0.01
+    U = lambda x, y, t: -np.cos(x) * np.sin(y) * np.exp(-2 * nu * t)
+    V = lambda x, y, t: np.sin(x) * np.cos(y) * np.exp(-2 * nu * t)
+    Pp = lambda x, y, t: -0.25 * (np.cos(2 * x) + np.cos(2 * y)) * np.exp(-4 * nu * t)
+    pt = (rng.uniform(0, 2 * pi, 50), rng.uniform(0, 2 * pi, 50), rng.uniform(0.1, 0.9, 50))
+    r1 = d1(U, pt, 2) + U(*pt) * d1(U, pt, 0) + V(*pt) * d1(U, pt, 1) + d1(Pp, pt, 0) - nu * (d2(U, pt, 0) + d2(U, pt, 1))
+    r2 = d1(V, pt, 2) + U(*pt) * d1(V, pt, 0) + V(*pt) * d1(V, pt, 1) + d1(Pp, pt, 1) - nu * (d2(V, pt, 0) + d2(V, pt, 1))
+    r3 = d1(U, pt, 0) + d1(V, pt, 1)
+    assert max(np.abs(r1).max(), np.abs(r2).max(), np.abs(r3).max()) < 1e-6
