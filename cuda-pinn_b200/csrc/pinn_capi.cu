@@ -19,6 +19,7 @@
 #include "pinn_device.cuh"
 #include "pinn_fused_fp32.cuh"
 #include "pinn_fused_tc.cuh"
+#include "pinn_fused_tc2.cuh"
 #include "pinn_fused_warp.cuh"
 #include "pinn_fused_mma.cuh"
 
@@ -444,6 +445,13 @@ struct pinn_ctx {
     long long wq_term_stride = 0;
     uint8_t* d_ring = nullptr; long long ring_per_cta = 0; int tc_defer_g = 0;   // deferred dW (width 256)
     int tc_ut = 8, nterms = 0, tc_threads = 0, tc_smem = 0, tc_tmem_cols = 0, grid_cap_tc = 0;
+    // producer / dW-server tensor-core kernel (pinn_fused_tc2.cuh): training launches of the interior set, widths 128 / 256
+    typedef void (*tc2_fn)(const NetDims, const Tc2Args);
+    tc2_fn kern_tc2 = nullptr;
+    int tc2_q = 0, tc2_nprod = 0, tc2_zdepth = 4, tc2_smem = 0;
+    __nv_bfloat16 *d_wf = nullptr, *d_wb = nullptr;
+    uint8_t *d_st_a = nullptr, *d_st_s = nullptr, *d_zring = nullptr;
+    unsigned int* d_tc2_flags = nullptr;
     // register-chained mma.sync kernel (width 20, PINN_PREC_BF16X3): interior set only
     typedef void (*mma_fn)(const NetDims, const MmaArgs);
     mma_fn kern_mma = nullptr;
@@ -717,7 +725,36 @@ static int configure_kernels(pinn_ctx* c) {
         if (occ > tmem_limit) occ = tmem_limit;
         c->grid_cap_tc = occ * c->num_sms;
         c->kernel_id = 100 + nterms;
-        if (H == 256 && nterms == 1 && nd.L >= 2) {
+        // Training launches of the six-channel nets at width 128 / 256 (BASELINE C4 / C5): producer + dW-server kernel,
+        // one cooperative launch with one CTA per SM.  PINN_TC2=0 keeps the round-1 kernel (it still serves evaluation).
+        {
+            const char* e2 = getenv("PINN_TC2");
+            const bool want = !(e2 && atoi(e2) == 0);
+            if (want && nterms == 1 && (H == 128 || H == 256) && nd.d_in == 3 && nd.n2 == 2 && nd.L >= 2) {
+                int q = H == 256 ? 5 : 8;
+                if (const char* eq = getenv("PINN_TC2_Q")) q = atoi(eq);
+                if (q < 1) q = 1;
+                while (q > 1 && c->num_sms - (nd.L - 1) * q < c->num_sms / 2) q--;
+                const int nprod = c->num_sms - (nd.L - 1) * q;
+                const int smem2 = tc2_smem_bytes(H, nd.L);
+                int coop = 0;
+                CUDA_TRY(c, "pinn_create", cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->cfg.device));
+                if (coop && nprod >= 8 && smem2 <= max_smem) {
+                    c->kern_tc2 = H == 128 ? fused_step_tc2<3, 2, 128> : fused_step_tc2<3, 2, 256>;
+                    CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+                    int occ2 = 0;
+                    CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, c->kern_tc2, 2 * H, smem2));
+                    if (occ2 < 1) c->kern_tc2 = nullptr;
+                    else {
+                        c->tc2_q = q; c->tc2_nprod = nprod; c->tc2_smem = smem2;
+                        if (const char* ez = getenv("PINN_TC2_ZD")) c->tc2_zdepth = atoi(ez);
+                        if (c->tc2_zdepth < 2) c->tc2_zdepth = 2;
+                        c->kernel_id = 110 + nterms;
+                    }
+                }
+            }
+        }
+        if (H == 256 && nterms == 1 && nd.L >= 2 && !c->kern_tc2) {
             c->tc_defer_g = 16;
             if (const char* e = getenv("PINN_TC_DEFER")) c->tc_defer_g = atoi(e);
             if (c->tc_defer_g < 0 || c->tc_defer_g > 64) c->tc_defer_g = 0;
@@ -829,6 +866,35 @@ static int launch_mma(pinn_ctx* c, const PointSet& interior, const PointSet* vse
     return PINN_OK;
 }
 
+// Producer / dW-server tensor-core kernel: one cooperative launch, one CTA per SM (the CTAs hand tiles to one another
+// through global flags, so all of them must be resident).  Uses partial rows [0, num_sms).
+static int launch_tc2(pinn_ctx* c, const PointSet& interior, int* rows_out) {
+    *rows_out = 0;
+    if (interior.n == 0) return PINN_OK;
+    Tc2Args a{};
+    a.params = c->d_params; a.set = interior; a.set.ntiles = tiles_of(interior.n, tc2::T);
+    a.partial = c->d_partial; a.row0 = 0;
+    a.wf = c->d_wf; a.wb = c->d_wb; a.stash_a = c->d_st_a; a.stash_s = c->d_st_s; a.zring = c->d_zring;
+    a.ready = c->d_tc2_flags; a.done = c->d_tc2_flags + (size_t)c->tc2_nprod * kFlagStride;
+    a.nprod = c->tc2_nprod; a.q = c->tc2_q; a.zdepth = c->tc2_zdepth;
+    CUDA_TRY(c, "pinn_train_step", cudaMemsetAsync(c->d_tc2_flags, 0, 2 * (size_t)c->tc2_nprod * kFlagStride * sizeof(unsigned int), c->stream));
+    const bool timed = c->prof && !c->capturing;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timed) {
+        CUDA_TRY(c, "pinn_train_step", cudaEventCreate(&e0)); CUDA_TRY(c, "pinn_train_step", cudaEventCreate(&e1));
+        CUDA_TRY(c, "pinn_train_step", cudaEventRecord(e0, c->stream));
+    }
+    NetDims nd = c->nd;
+    void* kargs[] = {&nd, &a};
+    CUDA_TRY(c, "pinn_train_step", cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(c->kern_tc2), dim3(c->num_sms),
+                                                               dim3(2 * c->nd.H), kargs, (size_t)c->tc2_smem, c->stream));
+    if (timed) { CUDA_TRY(c, "pinn_train_step", cudaEventRecord(e1, c->stream)); c->pending.emplace_back(e0, e1); }
+    c->last_grid = c->num_sms;
+    *rows_out = c->num_sms;
+    c->step_launches++;
+    return PINN_OK;
+}
+
 // Local part of a step: interior launch on the main stream, boundary + initial launch concurrently
 // on the auxiliary stream (disjoint partial rows), then the fixed-order reduction of all rows.
 static int run_local(pinn_ctx* c, int bump_step, bool do_reduce = true) {
@@ -839,7 +905,8 @@ static int run_local(pinn_ctx* c, int bump_step, bool do_reduce = true) {
         v[nv].ntiles = tiles_of(c->n_local[k], c->val_TP); nv++;
     }
     const bool mk = c->kern_mma != nullptr;
-    if (nv && !mk) {
+    const bool t2 = c->kern_tc2 != nullptr;              // cooperative launch on every SM: the value-only launch follows it on the same stream
+    if (nv && !mk && !t2) {
         CUDA_TRY(c, "pinn_train_step", cudaEventRecord(c->ev_fork, c->stream));
         CUDA_TRY(c, "pinn_train_step", cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
     }
@@ -847,14 +914,17 @@ static int run_local(pinn_ctx* c, int bump_step, bool do_reduce = true) {
     s.x = (mk && c->x_override) ? c->x_override : c->d_x[0];
     s.n = c->n_local[0]; s.scale = c->scale[0]; s.set = PINN_SET_INTERIOR; s.ntiles = tiles_of(s.n, c->TP);
     int grid_a = 0, grid_b = 0;
-    int rc = mk ? launch_mma(c, s, v, nv, &grid_a) : launch_fused(c, c->stream, true, &s, 1, 0, nullptr, nullptr, 0, &grid_a);
+    int rc = mk ? launch_mma(c, s, v, nv, &grid_a)
+                : (t2 ? launch_tc2(c, s, &grid_a) : launch_fused(c, c->stream, true, &s, 1, 0, nullptr, nullptr, 0, &grid_a));
     if (rc) return rc;
     if (nv && !mk) {
         const int row0 = c->rows_cap_a;                   // rows [0, rows_cap_a) belong to the interior launch
-        rc = launch_fused(c, c->stream2, false, v, nv, 0, nullptr, nullptr, row0, &grid_b);
+        rc = launch_fused(c, t2 ? c->stream : c->stream2, false, v, nv, 0, nullptr, nullptr, row0, &grid_b);
         if (rc) return rc;
-        CUDA_TRY(c, "pinn_train_step", cudaEventRecord(c->ev_join, c->stream2));
-        CUDA_TRY(c, "pinn_train_step", cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        if (!t2) {
+            CUDA_TRY(c, "pinn_train_step", cudaEventRecord(c->ev_join, c->stream2));
+            CUDA_TRY(c, "pinn_train_step", cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        }
     }
     c->rows_a = grid_a; c->rows_b = grid_b;
     if (!do_reduce) return PINN_OK;
@@ -908,6 +978,11 @@ static void refresh_wq(pinn_ctx* c, bool after_adam) {
     if (c->d_wfrag && c->nd.L >= 2 && !after_adam) {       // (the Adam kernels refresh this mirror themselves)
         const int n = (c->nd.L - 1) * 2 * 9 * c->mma_terms * 32;
         pack_wfrag_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->nd, c->d_params, c->d_wfrag, c->mma_terms, c->mma_f16);
+        c->step_launches++;
+    }
+    if (c->d_wf) {
+        const long long n2 = (long long)(c->nd.L - 1) * c->nd.H * c->nd.H;
+        pack_w2_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, c->stream>>>(c->nd, c->d_params, c->d_wf, c->d_wb);
         c->step_launches++;
     }
     if (!c->d_wq) return;
@@ -1116,6 +1191,7 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     if (c->grid_cap_val > c->rows_cap_a) c->rows_cap_a = c->grid_cap_val;      // pinn_forward uses the value kernel on rows A
     if (c->kern_warp && c->num_sms * c->warp_wpc > c->rows_cap_a) c->rows_cap_a = c->num_sms * c->warp_wpc;
     if (c->kern_mma && c->grid_cap_mma * kMmaWarps > c->rows_cap_a) c->rows_cap_a = c->grid_cap_mma * kMmaWarps;
+    if (c->kern_tc2 && c->num_sms > c->rows_cap_a) c->rows_cap_a = c->num_sms;
     c->rows_cap_b = c->grid_cap_val > c->grid_cap_tc ? c->grid_cap_val : c->grid_cap_tc;
     const size_t nrows = (size_t)c->rows_cap_a + c->rows_cap_b;
     c->stash_per_cta = (long long)nd.L * nd.C * nd.H * c->TP;   // the tensor-core kernel (16-point tiles) needs no more
@@ -1138,6 +1214,15 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
         TRY_C(cudaMalloc(&c->d_wq, (size_t)c->nterms * c->wq_term_stride * sizeof(__nv_bfloat16)));
     }
     if (c->tc_defer_g > 0) TRY_C(cudaMalloc(&c->d_ring, (size_t)c->grid_cap_tc * c->ring_per_cta));
+    if (c->kern_tc2) {
+        const size_t opb = (size_t)nd.H * 256, np = (size_t)c->tc2_nprod;
+        TRY_C(cudaMalloc(&c->d_wf, (size_t)(nd.L - 1) * nd.H * nd.H * sizeof(__nv_bfloat16)));
+        TRY_C(cudaMalloc(&c->d_wb, (size_t)(nd.L - 1) * nd.H * nd.H * sizeof(__nv_bfloat16)));
+        TRY_C(cudaMalloc(&c->d_st_a, np * nd.L * opb));
+        TRY_C(cudaMalloc(&c->d_st_s, np * nd.L * tc2::NGRP * nd.H * 8));
+        TRY_C(cudaMalloc(&c->d_zring, np * c->tc2_zdepth * opb));
+        TRY_C(cudaMalloc(&c->d_tc2_flags, 2 * np * kFlagStride * sizeof(unsigned int)));
+    }
     TRY_C(cudaMalloc(&c->d_loss, 8 * sizeof(float)));          // [0..3] loss record, [4] overflow flag word: one D2H copy per read-back
     TRY_C(cudaMalloc(&c->d_step, sizeof(unsigned long long)));
     TRY_C(cudaMalloc(&c->d_tail, sizeof(unsigned int)));
@@ -1175,6 +1260,7 @@ void pinn_destroy(pinn_ctx* c) {
     cudaFree(c->d_params); cudaFree(c->d_paramsT); cudaFree(c->d_m); cudaFree(c->d_v);
     cudaFree(c->d_gbuf); cudaFree(c->d_partial); cudaFree(c->d_stash); cudaFree(c->d_loss);
     cudaFree(c->d_step); cudaFree(c->d_wq); cudaFree(c->d_ring); cudaFree(c->d_wfrag);
+    cudaFree(c->d_wf); cudaFree(c->d_wb); cudaFree(c->d_st_a); cudaFree(c->d_st_s); cudaFree(c->d_zring); cudaFree(c->d_tc2_flags);
     for (int r = 0; r < kMaxP2PRanks; r++)
         if (c->peer_ptr[r] && c->peer_ptr[r] != c->d_xchg) cudaIpcCloseMemHandle(c->peer_ptr[r]);
     cudaFree(c->d_xchg); cudaFree(c->d_done); cudaFree(c->d_tail); cudaFree(c->d_beta_pow);
@@ -1595,8 +1681,11 @@ int pinn_profile_get(pinn_ctx* c, pinn_profile* out, int reset) {
     cudaSetDevice(c->cfg.device);
     drain_profile(c);
     out->launches = c->launches; out->step_kernel_ms = c->kernel_ms; out->step_kernel_count = c->kernel_count;
-    out->grid = c->last_grid; out->block = c->kern_tc ? c->tc_threads : (c->kern_warp ? c->warp_wpc * 32 : c->threads);
-    out->smem_bytes = c->kern_tc ? c->tc_smem : (c->kern_warp ? c->warp_smem : c->smem_full); out->kernel_id = c->kernel_id;
+    out->grid = c->last_grid;
+    // launch shape of the kernel the interior training launch runs (the mma.sync kernel used to report the FP32 kernel's)
+    out->block = c->kern_mma ? kMmaWarps * 32 : (c->kern_tc2 ? 2 * c->nd.H : (c->kern_tc ? c->tc_threads : (c->kern_warp ? c->warp_wpc * 32 : c->threads)));
+    out->smem_bytes = c->kern_mma ? c->mma_smem : (c->kern_tc2 ? c->tc2_smem : (c->kern_tc ? c->tc_smem : (c->kern_warp ? c->warp_smem : c->smem_full)));
+    out->kernel_id = c->kernel_id;
     if (reset) { c->launches = 0; c->kernel_ms = 0.0; c->kernel_count = 0; }
     return PINN_OK;
 }

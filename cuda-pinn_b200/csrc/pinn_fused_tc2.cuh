@@ -1,0 +1,631 @@
+// pinn_fused_tc2.cuh — round-2 tensor-core train step for the wide networks (width 128 / 256, six Taylor
+// channels: the Allen-Cahn / heat / Navier-Stokes nets of BASELINE C4 / C5), interior set, BF16 operands
+// with FP32 accumulation in TMEM.  One persistent cooperative launch, ONE CTA per SM, two roles:
+//
+//   PRODUCER CTAs (blockIdx < nprod) walk 21-point tiles through the whole step.  The contractions are
+//   "units as rows":            Z_l^T [j, n] = W_l^T [j, k] . A_{l-1}^T [k, n]        (forward)
+//                               Abar_{l-1}^T [k, n] = W_l [k, j] . Zbar_l^T [j, n]    (reverse)
+//   with n = 6 * point + channel (126 of the 128 operand columns carry data), M = 128 units per UMMA
+//   (two M-tiles at width 256), N = 128, K = the width.  TMEM lane = unit, so ONE THREAD owns every Taylor
+//   channel of every point of its unit: the tanh / Taylor forward, the reverse adjoint, the bias gradient,
+//   dW_1 and dW_{L+1} are thread-local straight out of tcgen05.ld — no shared-memory transposition, no
+//   shuffles, no block reduction.  A thread writes its results as 16-byte chunks of the NEXT operand
+//   ([n/8][unit][8 n] bf16: MN-major B operand of the forward / reverse UMMAs, K-major operand of dW).
+//   The stash for the reverse pass is that operand image itself: the reverse formulas are written in the
+//   layer OUTPUTS (a, a', a''),
+//        zbar''_i = s abar''_i          zbar'_i = s abar'_i - 4 a a'_i abar''_i
+//        zbar     = s abar - sum_i 2 a a'_i abar'_i - sum_i (2 a a''_i + 2 a'_i^2) abar''_i
+//   so the 64 KB image leaves by ONE cp.async.bulk store per layer (plus s = 1 - a^2 in bf16, whose relative
+//   accuracy bf16(a) cannot give).  12 + 2 bytes per (point, unit, layer) instead of 24 of FP32 (z', z'').
+//
+//   dW SERVER CTAs (blockIdx >= nprod; q per hidden->hidden layer) never see a point: a 256 x 256 FP32 dW_l
+//   is all of TMEM, so the producers cannot hold it next to their own accumulators, and flushing it per tile
+//   costs 12 KB of L2 atomics per point-layer.  Instead server (l, i) streams the two dW_l operand images
+//   (A_{l-1} from the stash, Zbar_l from a small ring) of its producers' tiles through a 3-stage
+//   cp.async.bulk pipeline and accumulates dW_l = A_{l-1}^T Zbar_l in TMEM over the WHOLE step; it is
+//   drained once, into the CTA's own partial row.  Hand-off is a pair of global flags per
+//   (producer, layer) (release / acquire at gpu scope); servers take their producers in a fixed order, so
+//   the summation order — and every bit of the result — is the same on every run.
+//
+// Reference: the reference has no network code (include/network.cuh is empty); the building blocks this
+// replaces are tensor::matmul (include/tensor.cuh:380-409) + kernel::matmul (include/device/kernel.cuh:68-83).
+#pragma once
+#include "pinn_device.cuh"
+#include "pinn_fused_fp32.cuh"
+#include "pinn_umma.cuh"
+
+namespace pinn {
+
+struct Tc2Args {
+    const float* params;
+    PointSet set;                  // interior points; set.ntiles = ceil(n / 21)
+    float* partial;                // [rows][PP]; this launch uses rows row0 + blockIdx.x
+    int row0;
+    const __nv_bfloat16* wf;       // forward mirror  [L-1][H/128][16 j-groups][H k][8 j]   (A operand, MN-major)
+    const __nv_bfloat16* wb;       // reverse mirror  [L-1][H/128][H/8 j-groups][128 k][8 j] (A operand, K-major)
+    uint8_t* stash_a;              // [nprod][L][H*256 B]   operand images A_1..A_L of the tile in flight
+    uint8_t* stash_s;              // [nprod][L][6][H][4] bf16   s = 1 - a^2
+    uint8_t* zring;                // [nprod][zdepth][H*256 B]  Zbar images on their way to the dW servers
+    unsigned int* ready;           // [nprod][kFlagStride]  ready[p][l] = t+1: Zbar_l (and A_{l-1}) of tile t are in memory
+    unsigned int* done;            // [nprod][kFlagStride]  done[p][l]  = t+1: server has both operands of tile t on chip
+    int nprod, q, zdepth;
+};
+constexpr int kFlagStride = kMaxLayers + 2;
+
+namespace tc2 {
+
+constexpr int T = 21, G = 4, NGRP = 6;     // points per tile, per group; groups per tile (the last holds one point)
+constexpr int OUTCOL = 256;                // TMEM columns of the output-layer accumulator
+
+// tanh and s = 1 - tanh^2 from one exp2 and one reciprocal (absolute error ~2e-7; s keeps its RELATIVE accuracy
+// for saturated units, which 1 - a*a cannot).
+__device__ __forceinline__ void tanh_s(float z, float& a, float& s) {
+    z = fminf(fmaxf(z, -15.0f), 15.0f);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    a = fmaf(-2.0f, r, 1.0f);
+    s = 4.0f * e * r * r;
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Bounded: a hand-off that has not happened after ~4e9 cycles (2 s; normal waits are microseconds) is a protocol
+// failure — trap, so the launch fails loudly instead of hanging the GPU.
+__device__ __forceinline__ void wait_ge(const unsigned* p, unsigned v) {
+    if (ld_acquire(p) >= v) return;
+    const long long t0 = clock64();
+    while (ld_acquire(p) < v) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// tiles of producer p when `ntiles` tiles are dealt round-robin to `nprod` producers
+__host__ __device__ __forceinline__ int tiles_of_producer(int ntiles, int p, int nprod) {
+    return p < ntiles ? (ntiles - p + nprod - 1) / nprod : 0;
+}
+
+}  // namespace tc2
+
+// Dynamic shared memory (bytes) the kernel needs for width H and depth L.
+inline int tc2_smem_bytes(int H, int L) {
+    const int slab = 128 * H * 2, opb = H * 256;
+    const int producer = 2 * slab + opb + H * 32 + 2 * L * H * 4 + 2 * 128 * 16 + 32 * 16;
+    const int server = 3 * opb;
+    return producer > server ? producer : server;
+}
+
+template <int DIN, int N2, int HT>
+__global__ void __launch_bounds__(2 * HT, 1)
+fused_step_tc2(const NetDims nd, const Tc2Args ta) {
+    using namespace tc2;
+    constexpr int NC = 1 + DIN + N2;
+    static_assert(NC == 6 && DIN == 3 && N2 == 2, "built for the six-channel (x, y, t) networks");
+    static_assert(HT == 128 || HT == 256, "width 128 or 256");
+    constexpr int H = HT, MT = H / 128;
+    constexpr uint32_t OPB = (uint32_t)H * 256u;        // operand image: [16 n-groups][H units][16 B]
+    constexpr uint32_t SLAB = 128u * H * 2u;            // one weight slab: 128 rows of the A operand x K = H
+    constexpr uint32_t CHS = (uint32_t)H * 16u;         // byte stride between n-chunks of an operand image
+    extern __shared__ __align__(128) uint8_t smem2_raw[];
+    uint8_t* const smem = smem2_raw;
+    __shared__ uint64_t wbar[2], mma_bar, out_bar, full_bar[3], empty_bar[3], fin_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int L = nd.L;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q4 = warp & 3, mt = (warp >> 2) % MT, half = (warp >> 2) / MT;
+    const int j = mt * 128 + q4 * 32 + lane;            // the unit (TMEM lane q4*32 + lane of M-tile mt) this thread owns
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 512u);
+    if (tid == 0) {
+        umma::mbar_init(&wbar[0], 1); umma::mbar_init(&wbar[1], 1);
+        umma::mbar_init(&mma_bar, 2); umma::mbar_init(&out_bar, 1); umma::mbar_init(&fin_bar, 1);
+        for (int i = 0; i < 3; i++) { umma::mbar_init(&full_bar[i], 1); umma::mbar_init(&empty_bar[i], 1); }
+        umma::mbar_fence_init();
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    float* part = ta.partial + (size_t)(ta.row0 + blockIdx.x) * nd.PP;
+    const int ntiles = ta.set.ntiles, P = ta.nprod;
+
+    if ((int)blockIdx.x >= P) {
+        // =====================================================================================
+        // dW server: dW_l = sum over its producers' tiles of A_{l-1}^T Zbar_l, accumulated in TMEM
+        // =====================================================================================
+        const int ci = (int)blockIdx.x - P, l = 2 + ci / ta.q, i0 = ci % ta.q;
+        constexpr uint32_t HALF = OPB / 2;              // 8 n-chunks of both operands per pipeline stage
+        bool any_work = false;
+        for (int p = i0; p < P; p += ta.q) any_work |= tiles_of_producer(ntiles, p, P) > 0;
+        if (warp == 0 && lane == 0) {                   // ---- loader ----
+            unsigned it = 0;
+            for (int t = 0;; t++) {
+                bool any = false;
+                for (int p = i0; p < P; p += ta.q) {
+                    if (t >= tiles_of_producer(ntiles, p, P)) continue;
+                    any = true;
+                    wait_ge(ta.ready + (size_t)p * kFlagStride + l, (unsigned)t + 1u);
+                    fence_proxy_async_all();
+                    const unsigned item = (unsigned)t * (unsigned)(L - 1) + (unsigned)(L - l);
+                    const uint8_t* srcA = ta.stash_a + ((size_t)p * L + (l - 2)) * OPB;          // A_{l-1}
+                    const uint8_t* srcZ = ta.zring + ((size_t)p * ta.zdepth + item % (unsigned)ta.zdepth) * OPB;
+                    for (int h = 0; h < 2; h++, it++) {
+                        const unsigned st = it % 3u;
+                        if (it >= 3u) umma::mbar_wait(&empty_bar[st], ((it / 3u) - 1u) & 1u);
+                        umma::mbar_expect_tx(&full_bar[st], 2 * HALF);
+                        umma::bulk_g2s(smem + (size_t)st * OPB, srcA + (size_t)h * HALF, HALF, &full_bar[st]);
+                        umma::bulk_g2s(smem + (size_t)st * OPB + HALF, srcZ + (size_t)h * HALF, HALF, &full_bar[st]);
+                    }
+                }
+                if (!any) break;
+            }
+        } else if (warp == 1 && lane == 0) {            // ---- MMA issuer ----
+            unsigned it = 0;
+            for (int t = 0;; t++) {
+                bool any = false;
+                for (int p = i0; p < P; p += ta.q) {
+                    if (t >= tiles_of_producer(ntiles, p, P)) continue;
+                    any = true;
+                    for (int h = 0; h < 2; h++, it++) {
+                        const unsigned st = it % 3u;
+                        umma::mbar_wait(&full_bar[st], (it / 3u) & 1u);
+                        umma::tc_fence_after();
+                        const uint32_t sa = umma::smem_u32(smem + (size_t)st * OPB), sz = sa + HALF;
+                        // both operands K-major over n: 8-column chunks CHS apart, 8 rows (units) 128 B apart
+                        #pragma unroll
+                        for (int m = 0; m < MT; m++)
+                            umma::gemm_issue(tmem + (uint32_t)(m * H), sa + (uint32_t)m * 2048u, CHS, 128, 2 * CHS,
+                                             sz, CHS, 128, 2 * CHS, umma::idesc_bf16(128, H, 0, 0), 4, it > 0 ? 1u : 0u);
+                        umma::mma_commit(&empty_bar[st]);
+                    }
+                    st_release(ta.done + (size_t)p * kFlagStride + l, (unsigned)t + 1u);   // both operand images are on chip
+                }
+                if (!any) break;
+            }
+            umma::mma_commit(&fin_bar);
+        }
+        umma::mbar_wait(&fin_bar, 0);
+        umma::tc_fence_after();
+        if (any_work) {                                 // drain: lane = fan-in unit k, columns = units j
+            float* dst = part + nd.offW[l] + (size_t)j * H;
+            for (int c = half * (H / 2); c < (half + 1) * (H / 2); c += 16) {
+                uint32_t r[16];
+                tmem_ld16_nowait(tmem + lane_addr + (uint32_t)(mt * H + c), r);
+                umma::tmem_ld_wait();
+                #pragma unroll
+                for (int v = 0; v < 4; v++)
+                    *reinterpret_cast<float4*>(dst + c + 4 * v) =
+                        make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                                    __uint_as_float(r[4 * v + 3]));
+            }
+        }
+        umma::tc_fence_before();
+        __syncthreads();
+        if (warp == 0) umma::tmem_dealloc(tmem, 512u);
+        return;
+    }
+
+    // =========================================================================================
+    // producer
+    // =========================================================================================
+    const int p = (int)blockIdx.x;
+    const int my_tiles = tiles_of_producer(ntiles, p, P);
+    uint8_t* Wb0 = smem;
+    uint8_t* opA = smem + 2 * SLAB;
+    uint8_t* wo16 = opA + OPB;                                   // output-layer B operand [2 o-groups][H][8 o] bf16
+    float* dbs = reinterpret_cast<float*>(wo16 + H * 32);        // [2 halves][L][H]: db_l sums of this CTA
+    float* ex = reinterpret_cast<float*>(opA);                   // [2 halves][6][H]: dW_1 / dW_{L+1} exchange after the last tile
+    float* ys = dbs + 2 * L * H;                                   // [128 n][4]: outputs y_o of column n
+    float* yb = ys + 128 * 4;                                    // [128 n][4]: seeds ybar_o of column n
+    float* xs = yb + 128 * 4;                                    // [32 points][4]
+    uint8_t* stA = ta.stash_a + (size_t)p * L * OPB;
+    uint2* stS = reinterpret_cast<uint2*>(ta.stash_s) + (size_t)p * L * NGRP * H;
+    uint8_t* zr = ta.zring + (size_t)p * ta.zdepth * OPB;
+    unsigned* rdy = ta.ready + (size_t)p * kFlagStride;
+    const unsigned* dn = ta.done + (size_t)p * kFlagStride;
+    const uint32_t op_addr = umma::smem_u32(opA), w_addr = umma::smem_u32(Wb0);
+
+    for (int i = tid; i < 2 * L * H; i += blockDim.x) dbs[i] = 0.0f;
+    for (int i = tid; i < 128 * 4; i += blockDim.x) { ys[i] = 0.0f; yb[i] = 0.0f; }
+    for (int i = tid; i < H * 16; i += blockDim.x) {             // wo16[(o/8)][k][o%8] = bf16(W_{L+1}[k][o])
+        const int og = i / (H * 8), k = (i / 8) % H, o = og * 8 + (i & 7);
+        reinterpret_cast<__nv_bfloat16*>(wo16)[i] = __float2bfloat16(o < nd.d_out ? __ldg(ta.params + nd.offW[L + 1] + k * nd.d_out + o) : 0.0f);
+    }
+    float dW1acc[DIN] = {0.0f, 0.0f, 0.0f}, dWoacc[3] = {0.0f, 0.0f, 0.0f};
+    float loss_acc = 0.0f, dbo_acc[3] = {0.0f, 0.0f, 0.0f};
+
+    // ---- weight slabs (thread 0): step sc of the per-tile schedule  fwd l = 2..L, then reverse l = L..2 ----
+    const long long nsteps = (long long)my_tiles * 2 * (L - 1);
+    auto slab_src = [&](long long sc, int m) -> const __nv_bfloat16* {
+        const int idx = (int)(sc % (2 * (L - 1)));
+        const bool fwd = idx < L - 1;
+        const int l = fwd ? 2 + idx : L - (idx - (L - 1));
+        return (fwd ? ta.wf : ta.wb) + ((size_t)(l - 2) * MT + m) * (size_t)(128 * H);
+    };
+    auto slab_buf = [&](long long sc, int m) { return MT == 2 ? m : (int)(sc & 1); };
+    auto slab_phase = [&](long long sc) { return MT == 2 ? (uint32_t)(sc & 1) : (uint32_t)((sc >> 1) & 1); };
+    auto request_step = [&](long long sc) {
+        if (sc >= nsteps) return;
+        #pragma unroll
+        for (int m = 0; m < MT; m++) {
+            const int b = slab_buf(sc, m);
+            umma::mbar_expect_tx(&wbar[b], SLAB);
+            umma::bulk_g2s(Wb0 + (size_t)b * SLAB, slab_src(sc, m), SLAB, &wbar[b]);
+        }
+    };
+    auto wait_step = [&](long long sc) {
+        #pragma unroll
+        for (int m = 0; m < MT; m++) umma::mbar_wait(&wbar[slab_buf(sc, m)], slab_phase(sc));
+    };
+    long long sc = 0;
+    uint32_t mma_phase = 0, out_phase = 0;
+    if (tid == 0) request_step(0);
+    __syncthreads();
+
+    // my column groups: half 0 owns groups 0..2 (12 points), half 1 groups 3..5 (8 points + the single-point tail)
+    const int g_lo = half * 3, g_hi = g_lo + 3;
+
+    // 24 (or 6) FP32 results of a group -> bf16 chunks of the operand image row of this unit
+    auto store_group = [&](int g, const float* out, int np) {
+        uint8_t* dst = opA + (size_t)(3 * g) * CHS + (size_t)j * 16;
+        if (np == G) {
+            #pragma unroll
+            for (int c = 0; c < 3; c++)
+                *reinterpret_cast<uint4*>(dst + (size_t)c * CHS) =
+                    make_uint4(pack2(out[8 * c], out[8 * c + 1]), pack2(out[8 * c + 2], out[8 * c + 3]),
+                               pack2(out[8 * c + 4], out[8 * c + 5]), pack2(out[8 * c + 6], out[8 * c + 7]));
+        } else {                                              // tail group: one point + two zero pad columns
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(out[0], out[1]), pack2(out[2], out[3]), pack2(out[4], out[5]), 0u);
+        }
+    };
+    // operand image row of this unit (chunks of group g) -> 24 (or 6) floats; src is shared or global memory
+    auto load_group = [&](const uint8_t* img, int g, float* v, int np, bool global) {
+        const uint8_t* src = img + (size_t)(3 * g) * CHS + (size_t)j * 16;
+        const int nch = np == G ? 3 : 1;
+        #pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (c < nch) {
+                uint4 w;
+                if (global) w = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)c * CHS));
+                else w = *reinterpret_cast<const uint4*>(src + (size_t)c * CHS);
+                v[8 * c + 0] = bf_lo(w.x); v[8 * c + 1] = bf_hi(w.x); v[8 * c + 2] = bf_lo(w.y); v[8 * c + 3] = bf_hi(w.y);
+                v[8 * c + 4] = bf_lo(w.z); v[8 * c + 5] = bf_hi(w.z); v[8 * c + 6] = bf_lo(w.w); v[8 * c + 7] = bf_hi(w.w);
+            }
+        }
+    };
+    // accumulator columns of group g of this unit's TMEM lane -> 24 (or 8) floats
+    auto load_acc = [&](int g, float* v, int np) {
+        uint32_t r[24];
+        const uint32_t ta0 = tmem + lane_addr + (uint32_t)(mt * 128 + 24 * g);
+        if (np == G) { tmem_ld16_nowait(ta0, r); tmem_ld8_nowait(ta0 + 16, r + 16); }
+        else tmem_ld8_nowait(ta0, r);
+        umma::tmem_ld_wait();
+        const int nv = np == G ? 24 : 8;
+        #pragma unroll
+        for (int i = 0; i < 24; i++) if (i < nv) v[i] = __uint_as_float(r[i]);
+    };
+    // forward tanh layer on one point: z (value, 3 first, 2 second tangents) -> a, a', a'' ; returns s
+    auto fwd_point = [&](const float* z, float bias, float* out) -> float {
+        float a, s;
+        tanh_s(z[0] + bias, a, s);
+        const float m2as = -2.0f * a * s;
+        out[0] = a;
+        #pragma unroll
+        for (int i = 0; i < DIN; i++) out[1 + i] = s * z[1 + i];
+        #pragma unroll
+        for (int i = 0; i < N2; i++) out[1 + DIN + i] = fmaf(m2as, z[1 + i] * z[1 + i], s * z[1 + DIN + i]);
+        return s;
+    };
+    // reverse through the tanh layer on one point, in the layer outputs av = (a, a', a''): ab -> zb ; returns zbar_0
+    auto bwd_point = [&](const float* av, float s, const float* ab, float* zb) -> float {
+        const float a = av[0], a2 = 2.0f * a;
+        float z0 = s * ab[0];
+        #pragma unroll
+        for (int i = 0; i < DIN; i++) {
+            float zp = s * ab[1 + i];
+            z0 = fmaf(-a2 * av[1 + i], ab[1 + i], z0);
+            if (i < N2) {
+                const float abpp = ab[1 + DIN + i];
+                zb[1 + DIN + i] = s * abpp;
+                zp = fmaf(-2.0f * a2 * av[1 + i], abpp, zp);
+                z0 = fmaf(-(a2 * av[1 + DIN + i] + 2.0f * av[1 + i] * av[1 + i]), abpp, z0);
+            }
+            zb[1 + i] = zp;
+        }
+        zb[0] = z0;
+        return z0;
+    };
+
+    for (int t = 0; t < my_tiles; t++) {
+        const unsigned long long base = (unsigned long long)(p + (long long)t * P) * T;
+        if (tid < T * DIN) {
+            const int pt = tid / DIN, k = tid - pt * DIN;
+            xs[pt * 4 + k] = (base + pt < ta.set.n) ? __ldg(ta.set.x + (base + pt) * DIN + k) : 0.0f;
+        }
+        __syncthreads();
+
+        // ---------------- layer 1 (K = d_in): CUDA cores ----------------
+        {
+            float w1[DIN];
+            #pragma unroll
+            for (int k = 0; k < DIN; k++) w1[k] = __ldg(ta.params + nd.offW[1] + k * H + j);
+            const float b1 = __ldg(ta.params + nd.offB[1] + j);
+            for (int g = g_lo; g < g_hi; g++) {
+                const int np = g == NGRP - 1 ? 1 : G;
+                float out[24], sv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                #pragma unroll
+                for (int pp = 0; pp < G; pp++) {
+                    if (pp < np) {
+                        const float4 x = *reinterpret_cast<const float4*>(xs + (G * g + pp) * 4);
+                        float z[NC];
+                        z[0] = fmaf(x.x, w1[0], fmaf(x.y, w1[1], x.z * w1[2]));
+                        #pragma unroll
+                        for (int i = 0; i < DIN; i++) z[1 + i] = w1[i];
+                        #pragma unroll
+                        for (int i = 0; i < N2; i++) z[1 + DIN + i] = 0.0f;
+                        sv[pp] = fwd_point(z, b1, out + NC * pp);
+                    }
+                }
+                store_group(g, out, np);
+                stS[(size_t)(0 * NGRP + g) * H + j] = make_uint2(pack2(sv[0], sv[1]), pack2(sv[2], sv[3]));
+            }
+        }
+        umma::fence_async_smem();
+        umma::tc_fence_before();
+        __syncthreads();
+
+        // thread 0: the operand image in opA is A_l — stash it (and for l < L it is a dW_{l+1} operand the servers read)
+        auto stash_image = [&](int l) {
+            if (l < L && t > 0) wait_ge(dn + (l + 1), (unsigned)t);     // server finished with A_l of the previous tile
+            umma::bulk_s2g(stA + (size_t)(l - 1) * OPB, opA, OPB);
+            umma::bulk_commit();
+        };
+        if (tid == 0) stash_image(1);
+
+        // ---------------- hidden layers 2..L: tensor cores ----------------
+        for (int l = 2; l <= L; l++, sc++) {
+            if (tid == 0) {
+                wait_step(sc);
+                umma::tc_fence_after();
+                #pragma unroll
+                for (int m = 0; m < MT; m++)      // A = W_l^T slab (MN-major: 8-unit groups CHS apart, 8 k rows 128 B apart)
+                    umma::gemm_issue(tmem + (uint32_t)(m * 128), w_addr + (uint32_t)slab_buf(sc, m) * SLAB, 128, CHS, 256,
+                                     op_addr, 128, CHS, 256, umma::idesc_bf16(128, 128, 1, 1), H / 16, 0u);
+                umma::mma_commit(&mma_bar);
+                if (MT == 1) request_step(sc + 1);
+                umma::bulk_wait_read_all();          // the stash store has read opA: the epilogue may overwrite it
+                mbar_arrive(&mma_bar);
+            }
+            umma::mbar_wait(&mma_bar, mma_phase); mma_phase ^= 1;
+            umma::tc_fence_after();
+            if (tid == 0 && MT == 2) request_step(sc + 1);
+            const float bl = __ldg(ta.params + nd.offB[l] + j);
+            for (int g = g_lo; g < g_hi; g++) {
+                const int np = g == NGRP - 1 ? 1 : G;
+                float z[24], out[24], sv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                load_acc(g, z, np);
+                #pragma unroll
+                for (int pp = 0; pp < G; pp++)
+                    if (pp < np) sv[pp] = fwd_point(z + NC * pp, bl, out + NC * pp);
+                store_group(g, out, np);
+                stS[(size_t)((l - 1) * NGRP + g) * H + j] = make_uint2(pack2(sv[0], sv[1]), pack2(sv[2], sv[3]));
+            }
+            umma::fence_async_smem();
+            umma::tc_fence_before();
+            __syncthreads();
+            if (tid == 0) stash_image(l);
+        }
+
+        // ---------------- output layer on the tensor cores: y[n, o] = A_L^T[n, k] . W_{L+1}[k, o] ----------------
+        if (tid == 0) {
+            umma::tc_fence_after();
+            umma::gemm_issue(tmem + OUTCOL, op_addr, 128, CHS, 256, umma::smem_u32(wo16), 128, CHS, 256,
+                             umma::idesc_bf16(128, 16, 1, 1), H / 16, 0u);
+            umma::mma_commit(&out_bar);
+            umma::bulk_wait_all();                   // every stash image of this tile is in memory (the reverse pass reads them back)
+            fence_proxy_async_all();
+        }
+        umma::mbar_wait(&out_bar, out_phase); out_phase ^= 1;
+        umma::tc_fence_after();
+        if (warp < 4) {                              // lane n = column n of the tile
+            float y4[4];
+            tmem_ld4(tmem + lane_addr + OUTCOL, y4);
+            *reinterpret_cast<float4*>(ys + tid * 4) = make_float4(y4[0], y4[1], y4[2], y4[3]);
+        }
+        umma::tc_fence_before();
+        __syncthreads();
+        if (tid < T) {                               // residual + seeds, one thread per point
+            float y[3][NC], ybar[3][NC], r[3], x[3];
+            #pragma unroll
+            for (int o = 0; o < 3; o++)
+                #pragma unroll
+                for (int c = 0; c < NC; c++)
+                    y[o][c] = (o < nd.d_out) ? ys[(NC * tid + c) * 4 + o] + (c == 0 ? __ldg(ta.params + nd.offB[L + 1] + o) : 0.0f) : 0.0f;
+            #pragma unroll
+            for (int k = 0; k < DIN; k++) x[k] = xs[tid * 4 + k];
+            float ss = pde_residual<NC>(nd, x, y, ta.set.scale, ybar, r);
+            const bool valid = base + tid < ta.set.n;
+            if (!valid) ss = 0.0f;
+            #pragma unroll
+            for (int c = 0; c < NC; c++)
+                *reinterpret_cast<float4*>(yb + (NC * tid + c) * 4) =
+                    valid ? make_float4(ybar[0][c], ybar[1][c], ybar[2][c], 0.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            loss_acc += ss;
+            if (valid) {
+                #pragma unroll
+                for (int o = 0; o < 3; o++) dbo_acc[o] += ybar[o][0];
+            }
+        }
+        __syncthreads();
+
+        // ---------------- reverse pass ----------------
+        float wo[3];
+        #pragma unroll
+        for (int o = 0; o < 3; o++) wo[o] = (o < nd.d_out) ? __ldg(ta.params + nd.offW[L + 1] + j * nd.d_out + o) : 0.0f;
+        for (int l = L; l >= 1; l--) {
+            float dbsum = 0.0f, dw1[DIN] = {0.0f, 0.0f, 0.0f};
+            for (int g = g_lo; g < g_hi; g++) {
+                const int np = g == NGRP - 1 ? 1 : G;
+                float av[24], ab[24], zb[24];
+                if (l == L) {
+                    // A_L is still the operand image in shared memory; Abar_L = ybar W_{L+1}^T and dW_{L+1} on the CUDA cores
+                    load_group(opA, g, av, np, false);
+                    #pragma unroll
+                    for (int i = 0; i < 24; i++) {
+                        if (i < NC * np) {
+                            const float4 s4 = *reinterpret_cast<const float4*>(yb + (24 * g + i) * 4);
+                            ab[i] = fmaf(wo[0], s4.x, fmaf(wo[1], s4.y, wo[2] * s4.z));
+                            dWoacc[0] = fmaf(av[i], s4.x, dWoacc[0]);
+                            dWoacc[1] = fmaf(av[i], s4.y, dWoacc[1]);
+                            dWoacc[2] = fmaf(av[i], s4.z, dWoacc[2]);
+                        }
+                    }
+                } else {
+                    load_acc(g, ab, np);
+                    load_group(stA + (size_t)(l - 1) * OPB, g, av, np, true);
+                }
+                const uint2 sw = __ldcg(stS + (size_t)((l - 1) * NGRP + g) * H + j);
+                const float sv[4] = {bf_lo(sw.x), bf_hi(sw.x), bf_lo(sw.y), bf_hi(sw.y)};
+                #pragma unroll
+                for (int pp = 0; pp < G; pp++) {
+                    if (pp < np) {
+                        dbsum += bwd_point(av + NC * pp, sv[pp], ab + NC * pp, zb + NC * pp);
+                        if (l == 1) {
+                            const float4 x = *reinterpret_cast<const float4*>(xs + (G * g + pp) * 4);
+                            dw1[0] += fmaf(x.x, zb[NC * pp], zb[NC * pp + 1]);
+                            dw1[1] += fmaf(x.y, zb[NC * pp], zb[NC * pp + 2]);
+                            dw1[2] += fmaf(x.z, zb[NC * pp], zb[NC * pp + 3]);
+                        }
+                    }
+                }
+                if (l > 1) store_group(g, zb, np);
+            }
+            dbs[(size_t)(half * L + (l - 1)) * H + j] += dbsum;
+            if (l == 1) {
+                #pragma unroll
+                for (int k = 0; k < DIN; k++) dW1acc[k] += dw1[k];
+                break;
+            }
+            umma::fence_async_smem();
+            umma::tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                wait_step(sc);
+                umma::tc_fence_after();
+                #pragma unroll
+                for (int m = 0; m < MT; m++)      // A = W_l rows (K-major: 8-unit chunks of j 2048 B apart, 8 k rows 128 B apart)
+                    umma::gemm_issue(tmem + (uint32_t)(m * 128), w_addr + (uint32_t)slab_buf(sc, m) * SLAB, 2048, 128, 4096,
+                                     op_addr, 128, CHS, 256, umma::idesc_bf16(128, 128, 0, 1), H / 16, 0u);
+                umma::mma_commit(&mma_bar);
+                if (MT == 1) request_step(sc + 1);
+                // Zbar_l image -> ring slot, then publish (A_{l-1} has been in memory since the forward pass)
+                const long long item = (long long)t * (L - 1) + (L - l);
+                if (item >= ta.zdepth) {
+                    const long long old = item - ta.zdepth;
+                    wait_ge(dn + (L - (int)(old % (L - 1))), (unsigned)(old / (L - 1)) + 1u);
+                }
+                umma::bulk_s2g(zr + (size_t)(item % ta.zdepth) * OPB, opA, OPB);
+                umma::bulk_commit();
+                umma::bulk_wait_all();
+                fence_proxy_async_all();
+                __threadfence();
+                st_release(rdy + l, (unsigned)t + 1u);
+                mbar_arrive(&mma_bar);
+            }
+            umma::mbar_wait(&mma_bar, mma_phase); mma_phase ^= 1;
+            umma::tc_fence_after();
+            if (tid == 0 && MT == 2) request_step(sc + 1);
+            sc++;
+        }
+        __syncthreads();                             // xs / yb are rewritten by the next tile
+    }
+
+    // ---------------- flush the per-CTA sums into this CTA's partial row (single owner per element) ----------------
+    __syncthreads();
+    for (int i = tid; i < L * H; i += blockDim.x) {
+        const int l = i / H + 1, jj = i - (l - 1) * H;
+        part[nd.offB[l] + jj] = dbs[(size_t)(l - 1) * H + jj] + dbs[(size_t)(L + (l - 1)) * H + jj];
+    }
+    // dW_1 [k][j] and dW_{L+1} [j][o]: the two column halves meet in shared memory, half 0 then half 1
+    #pragma unroll
+    for (int k = 0; k < DIN; k++) ex[(size_t)(half * 6 + k) * H + j] = dW1acc[k];
+    #pragma unroll
+    for (int o = 0; o < 3; o++) ex[(size_t)(half * 6 + 3 + o) * H + j] = dWoacc[o];
+    __syncthreads();
+    if (half == 0) {
+        #pragma unroll
+        for (int k = 0; k < DIN; k++) part[nd.offW[1] + k * H + j] = ex[(size_t)k * H + j] + ex[(size_t)(6 + k) * H + j];
+        for (int o = 0; o < nd.d_out; o++) part[nd.offW[L + 1] + j * nd.d_out + o] = ex[(size_t)(3 + o) * H + j] + ex[(size_t)(9 + o) * H + j];
+    }
+    if (warp == 0) {
+        float v[4] = {loss_acc, dbo_acc[0], dbo_acc[1], dbo_acc[2]};
+        #pragma unroll
+        for (int i = 0; i < 4; i++)
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+        if (lane == 0) {
+            part[nd.P + ta.set.set] = v[0];
+            for (int o = 0; o < nd.d_out; o++) part[nd.offB[L + 1] + o] = v[1 + o];
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 512u);
+}
+
+// BF16 mirrors of the hidden->hidden weights in the two slab layouts of Tc2Args (wf, wb).
+__global__ void pack_w2_kernel(const NetDims nd, const float* __restrict__ params, __nv_bfloat16* __restrict__ wf,
+                               __nv_bfloat16* __restrict__ wb) {
+    const int H = nd.H, MT = H / 128;
+    const long long n = (long long)(nd.L - 1) * H * H;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int l = (int)(i / ((long long)H * H)) + 2;
+    const int r = (int)(i % ((long long)H * H)), k = r / H, j = r - k * H;
+    const __nv_bfloat16 w = __float2bfloat16(params[nd.offW[l] + r]);
+    const size_t lbase = (size_t)(l - 2) * H * H;
+    // forward: [j/128][ (j%128)/8 ][k][j%8]
+    wf[lbase + (size_t)(j >> 7) * (128 * H) + (size_t)((j & 127) >> 3) * (H * 8) + (size_t)k * 8 + (j & 7)] = w;
+    // reverse: [k/128][ j/8 ][k%128][j%8]
+    wb[lbase + (size_t)(k >> 7) * (128 * H) + (size_t)(j >> 3) * (128 * 8) + (size_t)(k & 127) * 8 + (j & 7)] = w;
+    (void)MT;
+}
+
+}  // namespace pinn
