@@ -452,6 +452,7 @@ struct pinn_ctx {
     __nv_bfloat16 *d_wf = nullptr, *d_wb = nullptr;
     uint8_t *d_st_a = nullptr, *d_st_s = nullptr, *d_zring = nullptr;
     unsigned int* d_tc2_flags = nullptr;
+    long long* d_tc2_dbg = nullptr;                    // PINN_TC2_DBG=1: phase cycle counters of producer 0, printed at destroy
     // register-chained mma.sync kernel (width 20, PINN_PREC_BF16X3): interior set only
     typedef void (*mma_fn)(const NetDims, const MmaArgs);
     mma_fn kern_mma = nullptr;
@@ -731,7 +732,7 @@ static int configure_kernels(pinn_ctx* c) {
             const char* e2 = getenv("PINN_TC2");
             const bool want = !(e2 && atoi(e2) == 0);
             if (want && nterms == 1 && (H == 128 || H == 256) && nd.d_in == 3 && nd.n2 == 2 && nd.L >= 2) {
-                int q = H == 256 ? 5 : 8;
+                int q = H == 256 ? 4 : 7;                       // dW servers per hidden->hidden layer (measured best on C5 / C4)
                 if (const char* eq = getenv("PINN_TC2_Q")) q = atoi(eq);
                 if (q < 1) q = 1;
                 while (q > 1 && c->num_sms - (nd.L - 1) * q < c->num_sms / 2) q--;
@@ -876,7 +877,7 @@ static int launch_tc2(pinn_ctx* c, const PointSet& interior, int* rows_out) {
     a.partial = c->d_partial; a.row0 = 0;
     a.wf = c->d_wf; a.wb = c->d_wb; a.stash_a = c->d_st_a; a.stash_s = c->d_st_s; a.zring = c->d_zring;
     a.ready = c->d_tc2_flags; a.done = c->d_tc2_flags + (size_t)c->tc2_nprod * kFlagStride;
-    a.nprod = c->tc2_nprod; a.q = c->tc2_q; a.zdepth = c->tc2_zdepth;
+    a.nprod = c->tc2_nprod; a.q = c->tc2_q; a.zdepth = c->tc2_zdepth; a.dbg = c->d_tc2_dbg;
     CUDA_TRY(c, "pinn_train_step", cudaMemsetAsync(c->d_tc2_flags, 0, 2 * (size_t)c->tc2_nprod * kFlagStride * sizeof(unsigned int), c->stream));
     const bool timed = c->prof && !c->capturing;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1222,6 +1223,7 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
         TRY_C(cudaMalloc(&c->d_st_s, np * nd.L * tc2::NGRP * nd.H * 8));
         TRY_C(cudaMalloc(&c->d_zring, np * c->tc2_zdepth * opb));
         TRY_C(cudaMalloc(&c->d_tc2_flags, 2 * np * kFlagStride * sizeof(unsigned int)));
+        if (getenv("PINN_TC2_DBG")) { TRY_C(cudaMalloc(&c->d_tc2_dbg, 8 * sizeof(long long))); TRY_C(cudaMemsetAsync(c->d_tc2_dbg, 0, 8 * sizeof(long long), c->stream)); }
     }
     TRY_C(cudaMalloc(&c->d_loss, 8 * sizeof(float)));          // [0..3] loss record, [4] overflow flag word: one D2H copy per read-back
     TRY_C(cudaMalloc(&c->d_step, sizeof(unsigned long long)));
@@ -1255,6 +1257,13 @@ void pinn_destroy(pinn_ctx* c) {
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     if (c->stream) cudaStreamSynchronize(c->stream);
     drain_profile(c);
+    if (c->d_tc2_dbg) {
+        long long h[8] = {0};
+        if (cudaMemcpy(h, c->d_tc2_dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
+            fprintf(stderr, "[tc2 dbg] cycles of producer 0, last launch: fwd wait %lld  fwd epi %lld  out %lld  rev wait %lld  rev epi %lld  rev issue %lld  layer1 %lld  total %lld\n",
+                    h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+        cudaFree(c->d_tc2_dbg);
+    }
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
     for (int k = 0; k < 3; k++) cudaFree(c->d_x[k]);
     cudaFree(c->d_params); cudaFree(c->d_paramsT); cudaFree(c->d_m); cudaFree(c->d_v);

@@ -49,6 +49,7 @@ struct Tc2Args {
     unsigned int* ready;           // [nprod][kFlagStride]  ready[p][l] = t+1: Zbar_l (and A_{l-1}) of tile t are in memory
     unsigned int* done;            // [nprod][kFlagStride]  done[p][l]  = t+1: server has both operands of tile t on chip
     int nprod, q, zdepth;
+    long long* dbg;                // optional [8]: cycle counters of producer 0 (scripts/tc2_probe.py), or null
 };
 constexpr int kFlagStride = kMaxLayers + 2;
 
@@ -56,6 +57,8 @@ namespace tc2 {
 
 constexpr int T = 21, G = 4, NGRP = 6;     // points per tile, per group; groups per tile (the last holds one point)
 constexpr int OUTCOL = 256;                // TMEM columns of the output-layer accumulator
+// single-thread roles next to the epilogue work every thread does (one per warp, so their waits do not serialise)
+constexpr int kLoader = 32, kPublisher = 64, kWaiter = 96;
 
 // tanh and s = 1 - tanh^2 from one exp2 and one reciprocal (absolute error ~2e-7; s keeps its RELATIVE accuracy
 // for saturated units, which 1 - a*a cannot).
@@ -100,6 +103,20 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr) : "memory");
 }
+// tcgen05.wait::ld that names the registers it guards, so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_wait24(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23])
+                 :: "memory");
+}
+__device__ __forceinline__ void tmem_wait16(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
     uint32_t r[4];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
@@ -143,7 +160,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     constexpr uint32_t CHS = (uint32_t)H * 16u;         // byte stride between n-chunks of an operand image
     extern __shared__ __align__(128) uint8_t smem2_raw[];
     uint8_t* const smem = smem2_raw;
-    __shared__ uint64_t wbar[2], mma_bar, out_bar, full_bar[3], empty_bar[3], fin_bar;
+    __shared__ uint64_t wbar[2], mma_bar, out_bar, slab_free, full_bar[3], empty_bar[3], fin_bar;
     __shared__ uint32_t tmem_slot;
 
     const int L = nd.L;
@@ -155,7 +172,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     if (warp == 0) umma::tmem_alloc(&tmem_slot, 512u);
     if (tid == 0) {
         umma::mbar_init(&wbar[0], 1); umma::mbar_init(&wbar[1], 1);
-        umma::mbar_init(&mma_bar, 2); umma::mbar_init(&out_bar, 1); umma::mbar_init(&fin_bar, 1);
+        umma::mbar_init(&mma_bar, 2); umma::mbar_init(&out_bar, 1); umma::mbar_init(&fin_bar, 1); umma::mbar_init(&slab_free, 1);
         for (int i = 0; i < 3; i++) { umma::mbar_init(&full_bar[i], 1); umma::mbar_init(&empty_bar[i], 1); }
         umma::mbar_fence_init();
     }
@@ -249,10 +266,10 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     const int my_tiles = tiles_of_producer(ntiles, p, P);
     uint8_t* Wb0 = smem;
     uint8_t* opA = smem + 2 * SLAB;
-    uint8_t* wo16 = opA + OPB;                                   // output-layer B operand [2 o-groups][H][8 o] bf16
+    uint8_t* wo16 = opA + OPB;                                   // output-layer B operand [2 column groups][H][8] bf16: hi | lo of W_{L+1}
     float* dbs = reinterpret_cast<float*>(wo16 + H * 32);        // [2 halves][L][H]: db_l sums of this CTA
     float* ex = reinterpret_cast<float*>(opA);                   // [2 halves][6][H]: dW_1 / dW_{L+1} exchange after the last tile
-    float* ys = dbs + 2 * L * H;                                   // [128 n][4]: outputs y_o of column n
+    float* ys = dbs + 2 * L * H;                                 // [128 n][4]: outputs y_o of column n
     float* yb = ys + 128 * 4;                                    // [128 n][4]: seeds ybar_o of column n
     float* xs = yb + 128 * 4;                                    // [32 points][4]
     uint8_t* stA = ta.stash_a + (size_t)p * L * OPB;
@@ -264,82 +281,78 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
 
     for (int i = tid; i < 2 * L * H; i += blockDim.x) dbs[i] = 0.0f;
     for (int i = tid; i < 128 * 4; i += blockDim.x) { ys[i] = 0.0f; yb[i] = 0.0f; }
-    for (int i = tid; i < H * 16; i += blockDim.x) {             // wo16[(o/8)][k][o%8] = bf16(W_{L+1}[k][o])
-        const int og = i / (H * 8), k = (i / 8) % H, o = og * 8 + (i & 7);
-        reinterpret_cast<__nv_bfloat16*>(wo16)[i] = __float2bfloat16(o < nd.d_out ? __ldg(ta.params + nd.offW[L + 1] + k * nd.d_out + o) : 0.0f);
+    for (int i = tid; i < H * 16; i += blockDim.x) {             // columns 0..2: bf16(W_{L+1}[k][o]); columns 8..10: its bf16 remainder
+        const int og = i / (H * 8), k = (i / 8) % H, o = i & 7;
+        const float w = o < nd.d_out ? __ldg(ta.params + nd.offW[L + 1] + k * nd.d_out + o) : 0.0f;
+        const __nv_bfloat16 hi = __float2bfloat16(w);
+        reinterpret_cast<__nv_bfloat16*>(wo16)[i] = og == 0 ? hi : __float2bfloat16(w - __bfloat162float(hi));
     }
     float dW1acc[DIN] = {0.0f, 0.0f, 0.0f}, dWoacc[3] = {0.0f, 0.0f, 0.0f};
     float loss_acc = 0.0f, dbo_acc[3] = {0.0f, 0.0f, 0.0f};
 
     // ---- weight slabs (thread 0): step sc of the per-tile schedule  fwd l = 2..L, then reverse l = L..2 ----
     const long long nsteps = (long long)my_tiles * 2 * (L - 1);
-    auto slab_src = [&](long long sc, int m) -> const __nv_bfloat16* {
-        const int idx = (int)(sc % (2 * (L - 1)));
+    auto slab_src = [&](long long s_, int m) -> const __nv_bfloat16* {
+        const int idx = (int)(s_ % (2 * (L - 1)));
         const bool fwd = idx < L - 1;
         const int l = fwd ? 2 + idx : L - (idx - (L - 1));
         return (fwd ? ta.wf : ta.wb) + ((size_t)(l - 2) * MT + m) * (size_t)(128 * H);
     };
-    auto slab_buf = [&](long long sc, int m) { return MT == 2 ? m : (int)(sc & 1); };
-    auto slab_phase = [&](long long sc) { return MT == 2 ? (uint32_t)(sc & 1) : (uint32_t)((sc >> 1) & 1); };
-    auto request_step = [&](long long sc) {
-        if (sc >= nsteps) return;
+    auto slab_buf = [&](long long s_, int m) { return MT == 2 ? m : (int)(s_ & 1); };
+    auto slab_phase = [&](long long s_) { return MT == 2 ? (uint32_t)(s_ & 1) : (uint32_t)((s_ >> 1) & 1); };
+    auto request_step = [&](long long s_) {
+        if (s_ >= nsteps) return;
         #pragma unroll
         for (int m = 0; m < MT; m++) {
-            const int b = slab_buf(sc, m);
+            const int b = slab_buf(s_, m);
             umma::mbar_expect_tx(&wbar[b], SLAB);
-            umma::bulk_g2s(Wb0 + (size_t)b * SLAB, slab_src(sc, m), SLAB, &wbar[b]);
+            umma::bulk_g2s(Wb0 + (size_t)b * SLAB, slab_src(s_, m), SLAB, &wbar[b]);
         }
     };
-    auto wait_step = [&](long long sc) {
+    auto wait_step = [&](long long s_) {
         #pragma unroll
-        for (int m = 0; m < MT; m++) umma::mbar_wait(&wbar[slab_buf(sc, m)], slab_phase(sc));
+        for (int m = 0; m < MT; m++) umma::mbar_wait(&wbar[slab_buf(s_, m)], slab_phase(s_));
     };
     long long sc = 0;
     uint32_t mma_phase = 0, out_phase = 0;
     if (tid == 0) request_step(0);
     __syncthreads();
 
-    // my column groups: half 0 owns groups 0..2 (12 points), half 1 groups 3..5 (8 points + the single-point tail)
-    const int g_lo = half * 3, g_hi = g_lo + 3;
+    // This thread: unit j, column groups g0..g0+2 (4 points = 24 columns = 3 operand chunks each).  Half 1 ends with the
+    // single-point tail group (columns 120..125): its three phantom points are computed and masked, never stored or summed.
+    const int g0 = half * 3;
+    uint8_t* const op_row = opA + (size_t)j * 16;
+    const uint32_t tm_row = tmem + lane_addr + (uint32_t)(mt * 128);
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool dbg = ta.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    const long long t_begin = clock64();
 
-    // 24 (or 6) FP32 results of a group -> bf16 chunks of the operand image row of this unit
-    auto store_group = [&](int g, const float* out, int np) {
-        uint8_t* dst = opA + (size_t)(3 * g) * CHS + (size_t)j * 16;
-        if (np == G) {
-            #pragma unroll
-            for (int c = 0; c < 3; c++)
-                *reinterpret_cast<uint4*>(dst + (size_t)c * CHS) =
-                    make_uint4(pack2(out[8 * c], out[8 * c + 1]), pack2(out[8 * c + 2], out[8 * c + 3]),
-                               pack2(out[8 * c + 4], out[8 * c + 5]), pack2(out[8 * c + 6], out[8 * c + 7]));
-        } else {                                              // tail group: one point + two zero pad columns
-            *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(out[0], out[1]), pack2(out[2], out[3]), pack2(out[4], out[5]), 0u);
-        }
-    };
-    // operand image row of this unit (chunks of group g) -> 24 (or 6) floats; src is shared or global memory
-    auto load_group = [&](const uint8_t* img, int g, float* v, int np, bool global) {
-        const uint8_t* src = img + (size_t)(3 * g) * CHS + (size_t)j * 16;
-        const int nch = np == G ? 3 : 1;
+    auto point_ok = [&](int g, int pp) { return G * g + pp < T; };
+    auto chunk_ok = [&](int g, int c) { return 3 * g + c < 16; };
+    // 24 FP32 results of group g -> bf16 chunks of this unit's row of an operand image
+    // (row: this unit's row of an image in shared memory; grow: the same row of its copy in global memory, or null)
+    auto store_group = [&](uint8_t* row, uint8_t* grow, int g, const float* out) {
         #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            if (c < nch) {
-                uint4 w;
-                if (global) w = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)c * CHS));
-                else w = *reinterpret_cast<const uint4*>(src + (size_t)c * CHS);
-                v[8 * c + 0] = bf_lo(w.x); v[8 * c + 1] = bf_hi(w.x); v[8 * c + 2] = bf_lo(w.y); v[8 * c + 3] = bf_hi(w.y);
-                v[8 * c + 4] = bf_lo(w.z); v[8 * c + 5] = bf_hi(w.z); v[8 * c + 6] = bf_lo(w.w); v[8 * c + 7] = bf_hi(w.w);
+        for (int c = 0; c < 3; c++)
+            if (chunk_ok(g, c)) {
+                const uint4 w = make_uint4(pack2(out[8 * c], out[8 * c + 1]), pack2(out[8 * c + 2], out[8 * c + 3]),
+                                           pack2(out[8 * c + 4], out[8 * c + 5]), pack2(out[8 * c + 6], out[8 * c + 7]));
+                *reinterpret_cast<uint4*>(row + (size_t)(3 * g + c) * CHS) = w;
+                if (grow) __stcg(reinterpret_cast<uint4*>(grow + (size_t)(3 * g + c) * CHS), w);
             }
-        }
     };
-    // accumulator columns of group g of this unit's TMEM lane -> 24 (or 8) floats
-    auto load_acc = [&](int g, float* v, int np) {
+    auto unpack_chunk = [&](const uint4& w, float* v) {
+        v[0] = bf_lo(w.x); v[1] = bf_hi(w.x); v[2] = bf_lo(w.y); v[3] = bf_hi(w.y);
+        v[4] = bf_lo(w.z); v[5] = bf_hi(w.z); v[6] = bf_lo(w.w); v[7] = bf_hi(w.w);
+    };
+    // accumulator columns of group g of this unit's TMEM lane
+    auto load_acc = [&](int g, float* v) {
         uint32_t r[24];
-        const uint32_t ta0 = tmem + lane_addr + (uint32_t)(mt * 128 + 24 * g);
-        if (np == G) { tmem_ld16_nowait(ta0, r); tmem_ld8_nowait(ta0 + 16, r + 16); }
-        else tmem_ld8_nowait(ta0, r);
-        umma::tmem_ld_wait();
-        const int nv = np == G ? 24 : 8;
+        tmem_ld16_nowait(tm_row + (uint32_t)(24 * g), r);
+        tmem_ld8_nowait(tm_row + (uint32_t)(24 * g + 16), r + 16);
+        tmem_wait24(r);
         #pragma unroll
-        for (int i = 0; i < 24; i++) if (i < nv) v[i] = __uint_as_float(r[i]);
+        for (int i = 0; i < 24; i++) v[i] = __uint_as_float(r[i]);
     };
     // forward tanh layer on one point: z (value, 3 first, 2 second tangents) -> a, a', a'' ; returns s
     auto fwd_point = [&](const float* z, float bias, float* out) -> float {
@@ -372,9 +385,77 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
         zb[0] = z0;
         return z0;
     };
+    // forward epilogue of one group: pre-activations z (24) -> operand chunks (+ bf16 remainder image for layer L) + s stash
+    auto fwd_group = [&](int l, int g, const float* z, float bias, uint8_t* lo_row, uint8_t* grow) {
+        float out[24], sv[4];
+        #pragma unroll
+        for (int pp = 0; pp < G; pp++) sv[pp] = fwd_point(z + NC * pp, bias, out + NC * pp);
+        if (g == NGRP - 1) { out[6] = 0.0f; out[7] = 0.0f; }                 // pad columns 126, 127 of the tile
+        store_group(op_row, grow, g, out);
+        if (lo_row) {
+            float lo[24];
+            #pragma unroll
+            for (int i = 0; i < 24; i++) lo[i] = out[i] - __bfloat162float(__float2bfloat16(out[i]));
+            store_group(lo_row, nullptr, g, lo);
+        }
+        stS[(size_t)((l - 1) * NGRP + g) * H + j] = make_uint2(pack2(sv[0], sv[1]), pack2(sv[2], sv[3]));
+    };
+
+    // Hand-off rules (thread 0 checks the server flags BEFORE it lets the CTA into the epilogue that overwrites the data):
+    //   A_l   (stash image l, l < L; dW_{l+1} operand): rewritten by the forward epilogue of layer l of the NEXT tile ->
+    //         done[l+1] >= t before that epilogue;
+    //   Zbar_l (ring slot item % zdepth): written by the reverse epilogue of layer l -> the item zdepth earlier is done.
+    // Every thread writes its chunks to shared memory (next UMMA operand) AND to global memory (stash / ring); thread 0
+    // publishes ready[l] right after the block barrier that follows the epilogue (release at gpu scope is cumulative).
+    auto ring_wait = [&](int t_, int l) {
+        const unsigned item = (unsigned)t_ * (unsigned)(L - 1) + (unsigned)(L - l);
+        if (item >= (unsigned)ta.zdepth) {
+            const unsigned old = item - (unsigned)ta.zdepth;
+            wait_ge(dn + (L - (int)(old % (unsigned)(L - 1))), old / (unsigned)(L - 1) + 1u);
+        }
+    };
+    auto ring_row = [&](int t_, int l) -> uint8_t* {
+        const unsigned item = (unsigned)t_ * (unsigned)(L - 1) + (unsigned)(L - l);
+        return zr + (size_t)(item % (unsigned)ta.zdepth) * OPB + (size_t)j * 16;
+    };
+    // forward / reverse UMMAs of step s_ (thread 0): M-tile m as soon as its weight slab has landed; after the last UMMA of
+    // M-tile 0 a commit on slab_free lets the loader thread refill that buffer while M-tile 1 still runs.
+    auto issue_step = [&](long long s_, bool fwd) {
+        #pragma unroll
+        for (int m = 0; m < MT; m++) {
+            umma::mbar_wait(&wbar[slab_buf(s_, m)], slab_phase(s_));
+            umma::tc_fence_after();
+            if (fwd)       // A = W_l^T slab (MN-major: 8-unit groups CHS apart, 8 k rows 128 B apart)
+                umma::gemm_issue(tmem + (uint32_t)(m * 128), w_addr + (uint32_t)slab_buf(s_, m) * SLAB, 128, CHS, 256,
+                                 op_addr, 128, CHS, 256, umma::idesc_bf16(128, 128, 1, 1), H / 16, 0u);
+            else           // A = W_l rows (K-major: 8-unit chunks of j 2048 B apart, 8 k rows 128 B apart)
+                umma::gemm_issue(tmem + (uint32_t)(m * 128), w_addr + (uint32_t)slab_buf(s_, m) * SLAB, 2048, 128, 4096,
+                                 op_addr, 128, CHS, 256, umma::idesc_bf16(128, 128, 0, 1), H / 16, 0u);
+            if (MT == 2 && m == 0) umma::mma_commit(&slab_free);
+        }
+        umma::mma_commit(&mma_bar);
+        if (MT == 1) request_step(s_ + 1);
+    };
+    uint32_t free_phase = 0;                         // loader thread (tid 32), MT == 2
+    // loader thread: next step's slab for buffer 0 as soon as M-tile 0 is done, for buffer 1 when the whole step is
+    auto loader_first = [&](long long s_next) {
+        umma::mbar_wait(&slab_free, free_phase); free_phase ^= 1;
+        if (s_next < nsteps) {
+            umma::mbar_expect_tx(&wbar[0], SLAB);
+            umma::bulk_g2s(Wb0, slab_src(s_next, 0), SLAB, &wbar[0]);
+        }
+    };
+    auto loader_second = [&](long long s_next) {
+        if (s_next < nsteps) {
+            umma::mbar_expect_tx(&wbar[1], SLAB);
+            umma::bulk_g2s(Wb0 + SLAB, slab_src(s_next, 1), SLAB, &wbar[1]);
+        }
+    };
 
     for (int t = 0; t < my_tiles; t++) {
+        const long long c_t0 = dbg ? clock64() : 0;
         const unsigned long long base = (unsigned long long)(p + (long long)t * P) * T;
+        if (tid == kWaiter && t > 0) wait_ge(dn + 2, (unsigned)t);   // A_1 of the previous tile has been streamed by server 2
         if (tid < T * DIN) {
             const int pt = tid / DIN, k = tid - pt * DIN;
             xs[pt * 4 + k] = (base + pt < ta.set.n) ? __ldg(ta.set.x + (base + pt) * DIN + k) : 0.0f;
@@ -387,87 +468,77 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
             #pragma unroll
             for (int k = 0; k < DIN; k++) w1[k] = __ldg(ta.params + nd.offW[1] + k * H + j);
             const float b1 = __ldg(ta.params + nd.offB[1] + j);
-            for (int g = g_lo; g < g_hi; g++) {
-                const int np = g == NGRP - 1 ? 1 : G;
-                float out[24], sv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            #pragma unroll
+            for (int gi = 0; gi < 3; gi++) {
+                const int g = g0 + gi;
+                float z[24];
                 #pragma unroll
                 for (int pp = 0; pp < G; pp++) {
-                    if (pp < np) {
-                        const float4 x = *reinterpret_cast<const float4*>(xs + (G * g + pp) * 4);
-                        float z[NC];
-                        z[0] = fmaf(x.x, w1[0], fmaf(x.y, w1[1], x.z * w1[2]));
-                        #pragma unroll
-                        for (int i = 0; i < DIN; i++) z[1 + i] = w1[i];
-                        #pragma unroll
-                        for (int i = 0; i < N2; i++) z[1 + DIN + i] = 0.0f;
-                        sv[pp] = fwd_point(z, b1, out + NC * pp);
-                    }
+                    const float4 x = *reinterpret_cast<const float4*>(xs + ((G * g + pp) & 31) * 4);
+                    z[NC * pp] = fmaf(x.x, w1[0], fmaf(x.y, w1[1], x.z * w1[2]));
+                    #pragma unroll
+                    for (int i = 0; i < DIN; i++) z[NC * pp + 1 + i] = w1[i];
+                    #pragma unroll
+                    for (int i = 0; i < N2; i++) z[NC * pp + 1 + DIN + i] = 0.0f;
                 }
-                store_group(g, out, np);
-                stS[(size_t)(0 * NGRP + g) * H + j] = make_uint2(pack2(sv[0], sv[1]), pack2(sv[2], sv[3]));
+                fwd_group(1, g, z, b1, nullptr, stA + (size_t)j * 16);
             }
         }
         umma::fence_async_smem();
         umma::tc_fence_before();
         __syncthreads();
-
-        // thread 0: the operand image in opA is A_l — stash it (and for l < L it is a dW_{l+1} operand the servers read)
-        auto stash_image = [&](int l) {
-            if (l < L && t > 0) wait_ge(dn + (l + 1), (unsigned)t);     // server finished with A_l of the previous tile
-            umma::bulk_s2g(stA + (size_t)(l - 1) * OPB, opA, OPB);
-            umma::bulk_commit();
-        };
-        if (tid == 0) stash_image(1);
+        if (dbg) tacc[6] += clock64() - c_t0;
 
         // ---------------- hidden layers 2..L: tensor cores ----------------
+        uint8_t* lo_img = Wb0;                       // bf16 remainder of A_L: in a weight buffer that is idle around the output layer
         for (int l = 2; l <= L; l++, sc++) {
-            if (tid == 0) {
-                wait_step(sc);
-                umma::tc_fence_after();
-                #pragma unroll
-                for (int m = 0; m < MT; m++)      // A = W_l^T slab (MN-major: 8-unit groups CHS apart, 8 k rows 128 B apart)
-                    umma::gemm_issue(tmem + (uint32_t)(m * 128), w_addr + (uint32_t)slab_buf(sc, m) * SLAB, 128, CHS, 256,
-                                     op_addr, 128, CHS, 256, umma::idesc_bf16(128, 128, 1, 1), H / 16, 0u);
-                umma::mma_commit(&mma_bar);
-                if (MT == 1) request_step(sc + 1);
-                umma::bulk_wait_read_all();          // the stash store has read opA: the epilogue may overwrite it
+            const long long c_a = dbg ? clock64() : 0;
+            if (tid == 0) issue_step(sc, true);
+            if (tid == kWaiter) {
+                if (l < L && t > 0) wait_ge(dn + (l + 1), (unsigned)t);   // A_l of the previous tile may be overwritten
                 mbar_arrive(&mma_bar);
             }
+            if (MT == 2 && tid == kLoader && l < L) loader_first(sc + 1);
+            if (MT == 2 && tid == kLoader && l == L) { umma::mbar_wait(&slab_free, free_phase); free_phase ^= 1; }
+            const float bl = __ldg(ta.params + nd.offB[l] + j);
             umma::mbar_wait(&mma_bar, mma_phase); mma_phase ^= 1;
             umma::tc_fence_after();
-            if (tid == 0 && MT == 2) request_step(sc + 1);
-            const float bl = __ldg(ta.params + nd.offB[l] + j);
-            for (int g = g_lo; g < g_hi; g++) {
-                const int np = g == NGRP - 1 ? 1 : G;
-                float z[24], out[24], sv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                load_acc(g, z, np);
-                #pragma unroll
-                for (int pp = 0; pp < G; pp++)
-                    if (pp < np) sv[pp] = fwd_point(z + NC * pp, bl, out + NC * pp);
-                store_group(g, out, np);
-                stS[(size_t)((l - 1) * NGRP + g) * H + j] = make_uint2(pack2(sv[0], sv[1]), pack2(sv[2], sv[3]));
+            if (MT == 2 && tid == kLoader && l < L) loader_second(sc + 1);
+            if (l == L) lo_img = Wb0 + (MT == 2 ? 0 : (size_t)(sc & 1) * SLAB);
+            const long long c_b = dbg ? clock64() : 0;
+            #pragma unroll
+            for (int gi = 0; gi < 3; gi++) {
+                float z[24];
+                load_acc(g0 + gi, z);
+                fwd_group(l, g0 + gi, z, bl, l == L ? lo_img + (size_t)j * 16 : nullptr,
+                          l < L ? stA + (size_t)(l - 1) * OPB + (size_t)j * 16 : nullptr);
             }
             umma::fence_async_smem();
             umma::tc_fence_before();
             __syncthreads();
-            if (tid == 0) stash_image(l);
+            if (dbg) { const long long c_c = clock64(); tacc[0] += c_b - c_a; tacc[1] += c_c - c_b; }
         }
 
-        // ---------------- output layer on the tensor cores: y[n, o] = A_L^T[n, k] . W_{L+1}[k, o] ----------------
+        // ---------------- output layer on the tensor cores: y[n, :] = (A_L hi + lo)^T[n, k] . [W_{L+1} hi | lo][k, :] ----------------
+        const long long c_o = dbg ? clock64() : 0;
         if (tid == 0) {
             umma::tc_fence_after();
             umma::gemm_issue(tmem + OUTCOL, op_addr, 128, CHS, 256, umma::smem_u32(wo16), 128, CHS, 256,
                              umma::idesc_bf16(128, 16, 1, 1), H / 16, 0u);
+            umma::gemm_issue(tmem + OUTCOL, umma::smem_u32(lo_img), 128, CHS, 256, umma::smem_u32(wo16), 128, CHS, 256,
+                             umma::idesc_bf16(128, 16, 1, 1), H / 16, 1u);
             umma::mma_commit(&out_bar);
-            umma::bulk_wait_all();                   // every stash image of this tile is in memory (the reverse pass reads them back)
-            fence_proxy_async_all();
         }
         umma::mbar_wait(&out_bar, out_phase); out_phase ^= 1;
         umma::tc_fence_after();
+        if (MT == 2 && tid == kLoader) { loader_second(sc); if (sc < nsteps) { umma::mbar_expect_tx(&wbar[0], SLAB); umma::bulk_g2s(Wb0, slab_src(sc, 0), SLAB, &wbar[0]); } }
         if (warp < 4) {                              // lane n = column n of the tile
-            float y4[4];
-            tmem_ld4(tmem + lane_addr + OUTCOL, y4);
-            *reinterpret_cast<float4*>(ys + tid * 4) = make_float4(y4[0], y4[1], y4[2], y4[3]);
+            uint32_t r[16];
+            tmem_ld16_nowait(tmem + lane_addr + OUTCOL, r);
+            tmem_wait16(r);
+            *reinterpret_cast<float4*>(ys + tid * 4) =
+                make_float4(__uint_as_float(r[0]) + __uint_as_float(r[8]), __uint_as_float(r[1]) + __uint_as_float(r[9]),
+                            __uint_as_float(r[2]) + __uint_as_float(r[10]), 0.0f);
         }
         umma::tc_fence_before();
         __syncthreads();
@@ -493,88 +564,110 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
                 for (int o = 0; o < 3; o++) dbo_acc[o] += ybar[o][0];
             }
         }
+        if (tid == kWaiter) ring_wait(t, L);         // ring slot of Zbar_L
         __syncthreads();
+        if (dbg) tacc[2] += clock64() - c_o;
 
         // ---------------- reverse pass ----------------
         float wo[3];
         #pragma unroll
         for (int o = 0; o < 3; o++) wo[o] = (o < nd.d_out) ? __ldg(ta.params + nd.offW[L + 1] + j * nd.d_out + o) : 0.0f;
+        // Stash of reverse step l (s, and the layer outputs A_l): fetched one step ahead — it does not depend on the UMMA in
+        // flight, so its L2 latency hides behind the block barrier and the UMMA.
+        uint4 pa[3][3]; uint2 ps[3];
+        auto prefetch_stash = [&](int l) {
+            #pragma unroll
+            for (int gi = 0; gi < 3; gi++) {
+                const int g = g0 + gi;
+                ps[gi] = __ldcg(stS + (size_t)((l - 1) * NGRP + g) * H + j);
+                #pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    pa[gi][c] = make_uint4(0u, 0u, 0u, 0u);
+                    if (chunk_ok(g, c)) {
+                        if (l < L) pa[gi][c] = __ldcg(reinterpret_cast<const uint4*>(stA + (size_t)(l - 1) * OPB + (size_t)(3 * g + c) * CHS + (size_t)j * 16));
+                        else pa[gi][c] = *reinterpret_cast<const uint4*>(op_row + (size_t)(3 * g + c) * CHS);   // A_L is still the operand image
+                    }
+                }
+            }
+        };
+        prefetch_stash(L);
         for (int l = L; l >= 1; l--) {
+            const long long c_d = dbg ? clock64() : 0;
+            if (l < L) {
+                if (MT == 2 && tid == kLoader) loader_first(sc);
+                umma::mbar_wait(&mma_bar, mma_phase); mma_phase ^= 1;
+                umma::tc_fence_after();
+                if (MT == 2 && tid == kLoader) loader_second(sc);
+            }
+            const long long c_e = dbg ? clock64() : 0;
             float dbsum = 0.0f, dw1[DIN] = {0.0f, 0.0f, 0.0f};
-            for (int g = g_lo; g < g_hi; g++) {
-                const int np = g == NGRP - 1 ? 1 : G;
+            uint8_t* const zrow = l > 1 ? ring_row(t, l) : nullptr;
+            #pragma unroll
+            for (int gi = 0; gi < 3; gi++) {
+                const int g = g0 + gi;
                 float av[24], ab[24], zb[24];
+                #pragma unroll
+                for (int c = 0; c < 3; c++) unpack_chunk(pa[gi][c], av + 8 * c);
                 if (l == L) {
-                    // A_L is still the operand image in shared memory; Abar_L = ybar W_{L+1}^T and dW_{L+1} on the CUDA cores
-                    load_group(opA, g, av, np, false);
+                    // Abar_L = ybar W_{L+1}^T and dW_{L+1} on the CUDA cores
                     #pragma unroll
                     for (int i = 0; i < 24; i++) {
-                        if (i < NC * np) {
-                            const float4 s4 = *reinterpret_cast<const float4*>(yb + (24 * g + i) * 4);
-                            ab[i] = fmaf(wo[0], s4.x, fmaf(wo[1], s4.y, wo[2] * s4.z));
-                            dWoacc[0] = fmaf(av[i], s4.x, dWoacc[0]);
-                            dWoacc[1] = fmaf(av[i], s4.y, dWoacc[1]);
-                            dWoacc[2] = fmaf(av[i], s4.z, dWoacc[2]);
-                        }
+                        const float4 s4 = *reinterpret_cast<const float4*>(yb + ((24 * g + i) & 127) * 4);
+                        ab[i] = fmaf(wo[0], s4.x, fmaf(wo[1], s4.y, wo[2] * s4.z));
+                        const float a_ok = point_ok(g, i / NC) ? av[i] : 0.0f;
+                        dWoacc[0] = fmaf(a_ok, s4.x, dWoacc[0]);
+                        dWoacc[1] = fmaf(a_ok, s4.y, dWoacc[1]);
+                        dWoacc[2] = fmaf(a_ok, s4.z, dWoacc[2]);
                     }
                 } else {
-                    load_acc(g, ab, np);
-                    load_group(stA + (size_t)(l - 1) * OPB, g, av, np, true);
+                    load_acc(g, ab);
                 }
-                const uint2 sw = __ldcg(stS + (size_t)((l - 1) * NGRP + g) * H + j);
-                const float sv[4] = {bf_lo(sw.x), bf_hi(sw.x), bf_lo(sw.y), bf_hi(sw.y)};
+                const float sv[4] = {bf_lo(ps[gi].x), bf_hi(ps[gi].x), bf_lo(ps[gi].y), bf_hi(ps[gi].y)};
                 #pragma unroll
                 for (int pp = 0; pp < G; pp++) {
-                    if (pp < np) {
-                        dbsum += bwd_point(av + NC * pp, sv[pp], ab + NC * pp, zb + NC * pp);
+                    const float z0 = bwd_point(av + NC * pp, sv[pp], ab + NC * pp, zb + NC * pp);
+                    if (point_ok(g, pp)) {
+                        dbsum += z0;
                         if (l == 1) {
-                            const float4 x = *reinterpret_cast<const float4*>(xs + (G * g + pp) * 4);
-                            dw1[0] += fmaf(x.x, zb[NC * pp], zb[NC * pp + 1]);
-                            dw1[1] += fmaf(x.y, zb[NC * pp], zb[NC * pp + 2]);
-                            dw1[2] += fmaf(x.z, zb[NC * pp], zb[NC * pp + 3]);
+                            const float4 x = *reinterpret_cast<const float4*>(xs + ((G * g + pp) & 31) * 4);
+                            dw1[0] += fmaf(x.x, z0, zb[NC * pp + 1]);
+                            dw1[1] += fmaf(x.y, z0, zb[NC * pp + 2]);
+                            dw1[2] += fmaf(x.z, z0, zb[NC * pp + 3]);
                         }
                     }
                 }
-                if (l > 1) store_group(g, zb, np);
+                if (g == NGRP - 1) { zb[6] = 0.0f; zb[7] = 0.0f; }
+                if (l > 1) store_group(op_row, zrow, g, zb);
             }
             dbs[(size_t)(half * L + (l - 1)) * H + j] += dbsum;
             if (l == 1) {
                 #pragma unroll
                 for (int k = 0; k < DIN; k++) dW1acc[k] += dw1[k];
+                if (dbg) { const long long c_f = clock64(); tacc[3] += c_e - c_d; tacc[4] += c_f - c_e; }
                 break;
             }
+            prefetch_stash(l - 1);
             umma::fence_async_smem();
             umma::tc_fence_before();
             __syncthreads();
-            if (tid == 0) {
-                wait_step(sc);
-                umma::tc_fence_after();
-                #pragma unroll
-                for (int m = 0; m < MT; m++)      // A = W_l rows (K-major: 8-unit chunks of j 2048 B apart, 8 k rows 128 B apart)
-                    umma::gemm_issue(tmem + (uint32_t)(m * 128), w_addr + (uint32_t)slab_buf(sc, m) * SLAB, 2048, 128, 4096,
-                                     op_addr, 128, CHS, 256, umma::idesc_bf16(128, 128, 0, 1), H / 16, 0u);
-                umma::mma_commit(&mma_bar);
-                if (MT == 1) request_step(sc + 1);
-                // Zbar_l image -> ring slot, then publish (A_{l-1} has been in memory since the forward pass)
-                const long long item = (long long)t * (L - 1) + (L - l);
-                if (item >= ta.zdepth) {
-                    const long long old = item - ta.zdepth;
-                    wait_ge(dn + (L - (int)(old % (L - 1))), (unsigned)(old / (L - 1)) + 1u);
-                }
-                umma::bulk_s2g(zr + (size_t)(item % ta.zdepth) * OPB, opA, OPB);
-                umma::bulk_commit();
-                umma::bulk_wait_all();
-                fence_proxy_async_all();
+            const long long c_f = dbg ? clock64() : 0;
+            if (tid == 0) issue_step(sc, false);
+            if (tid == kPublisher) {                     // Zbar_l (and, since the forward pass, A_{l-1}) are in memory
                 __threadfence();
                 st_release(rdy + l, (unsigned)t + 1u);
+            }
+            if (tid == kWaiter) {
+                if (l > 2) ring_wait(t, l - 1);          // ring slot of Zbar_{l-1}, written by the next epilogue
                 mbar_arrive(&mma_bar);
             }
-            umma::mbar_wait(&mma_bar, mma_phase); mma_phase ^= 1;
-            umma::tc_fence_after();
-            if (tid == 0 && MT == 2) request_step(sc + 1);
             sc++;
+            if (dbg) { const long long c_g = clock64(); tacc[3] += c_e - c_d; tacc[4] += c_f - c_e; tacc[5] += c_g - c_f; }
         }
         __syncthreads();                             // xs / yb are rewritten by the next tile
+    }
+    if (dbg) {
+        tacc[7] = clock64() - t_begin;
+        for (int i = 0; i < 8; i++) ta.dbg[i] = tacc[i];
     }
 
     // ---------------- flush the per-CTA sums into this CTA's partial row (single owner per element) ----------------

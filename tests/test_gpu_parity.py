@@ -254,7 +254,10 @@ def test_tensor_core_path_against_float64_oracle(P, oracle, pde, width, depth, n
         out = net.loss_grad()
         g = net.get_grads()
         Y, r = net.residual(xs[0][:100])
-        assert net.profile_get()["kernel_id"] == 100 + (2 if prec == 1 else 1)      # the tcgen05 kernel really ran
+        # the tcgen05 kernel really ran: 10x = tile-per-CTA kernel (pinn_fused_tc.cuh), 11x = producer / dW-server kernel
+        # (pinn_fused_tc2.cuh: BF16, six-channel nets of width 128 / 256, depth >= 2)
+        tc2 = prec == 2 and width in (128, 256) and pde in (2, 3, 4) and depth >= 2
+        assert net.profile_get()["kernel_id"] == (110 if tc2 else 100) + (2 if prec == 1 else 1)
     assert abs(out["loss"] / l_ref - 1) < tol_l
     assert rel_err(g, g_ref) < tol_g
     Y_ref, _ = oracle.residual(ocfg, w.astype(np.float64), xs[0][:100])
@@ -271,6 +274,58 @@ def test_tensor_core_bf16x3_training_tracks_the_oracle(P, oracle):
     p_ref, _, _, l_ref, _ = oracle.train(ocfg, w0.astype(np.float64), 30, dtype=np.float64)
     assert np.abs(losses / l_ref[:, 0] - 1).max() < 1e-4
     assert np.abs(w - p_ref).max() < 1e-4
+
+
+# Producer / dW-server kernel (pinn_fused_tc2.cuh): several tiles per producer CTA, ragged last tile, fewer tiles than
+# producers, both widths, every six-channel PDE; gradients bit-reproducible from run to run (servers take their
+# producers in a fixed order) and equal to the round-1 tile-per-CTA kernel's within the BF16 bar.
+TC2_CASES = [  # pde, width, depth, n_interior
+    (4, 256, 8, 21 * 148 * 2 + 5), (4, 256, 2, 20), (2, 128, 6, 21 * 200 + 1), (3, 128, 4, 30011), (3, 256, 3, 9000), (4, 128, 2, 1)]
+
+
+@pytest.mark.parametrize("pde,width,depth,n", TC2_CASES)
+def test_producer_server_tensor_kernel_against_float64_oracle(P, oracle, pde, width, depth, n):
+    ocfg = oracle.make_config(pde, width, depth, n, 300, 300)
+    xs = [oracle.sample(ocfg, k) for k in range(3)]
+    rng = np.random.default_rng(2)
+    w = (oracle.init_params(ocfg) + 0.02 * rng.standard_normal(oracle.num_params(ocfg))).astype(np.float32)
+    g_ref, s_ref = oracle.loss_grad(ocfg, w.astype(np.float64), *xs)
+    l_ref = oracle.loss_from_sums(ocfg, s_ref)[0]
+    res = []
+    for _ in range(2):
+        with P.Network(pcfg(P, ocfg, precision=2)) as net:
+            net.set_params(w)
+            out = net.loss_grad()
+            res.append((out["loss"], net.get_grads()))
+            assert net.profile_get()["kernel_id"] == 111
+    # BF16 bars (stated above); the eight-layer width-256 net accumulates one BF16 rounding per layer and channel and
+    # measures 1.6e-2 on its largest gradient entries (the round-1 kernel measures 9e-3..1.6e-2 on the same nets): 2e-2 there
+    assert abs(res[0][0] / l_ref - 1) < 5e-3
+    assert rel_err(res[0][1], g_ref) < (2e-2 if depth >= 8 else 1e-2)
+    assert res[0][0] == res[1][0] and np.array_equal(res[0][1].view(np.uint32), res[1][1].view(np.uint32))
+
+
+@pytest.mark.parametrize("which,n", [(4, 4096), (5, 2048)])
+def test_wide_nets_bf16_trajectory_tracks_the_oracle(P, oracle, which, n):
+    """100 Adam steps of the C4 (3->[128x6]->1 Allen-Cahn) and C5 (3->[256x8]->3 Navier-Stokes) networks on the precision
+    `bench.py --precision auto` uses for them (BF16 on the producer / dW-server kernel) vs the float64 oracle.
+    Stated tolerances for this precision class: Adam's first steps (lr 1e-3 on a fresh net) send the loss through a
+    transient that amplifies any gradient perturbation — 1e-1 relative over the first 20 steps; 1e-2 from step 20 on;
+    parameters 1e-2 absolute after 100 steps (a parameter moves at most 0.1 over the run; measured 4e-3 on C4).
+    Measured on B200: see the assertion messages / DESIGN.md (precision table)."""
+    ocfg = oracle.baseline_config(which, n_interior=n, n_boundary=256, n_initial=256)
+    with P.Network(pcfg(P, ocfg, precision=2)) as net:
+        assert net.profile_get()["kernel_id"] == 111
+        w0 = net.get_params()
+        losses = np.array([net.train_step()["loss"] for _ in range(100)])
+        w = net.get_params()
+    p_ref, _, _, l_ref, _ = oracle.train(ocfg, w0.astype(np.float64), 100, dtype=np.float64)
+    rel = np.abs(losses / l_ref[:, 0] - 1)
+    dw = np.abs(w - p_ref).max()
+    print(f"C{which} bf16 trajectory: loss rel first 20 steps {rel[:20].max():.2e}, steps 20..99 {rel[20:].max():.2e}, params {dw:.2e}")
+    assert rel[:20].max() < 1e-1, rel[:20].max()
+    assert rel[20:].max() < 1e-2, rel[20:].max()
+    assert dw < 1e-2, dw
 
 
 def test_tensor_core_rejects_unsupported_widths(P, oracle):
