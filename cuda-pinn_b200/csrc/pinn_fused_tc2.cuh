@@ -49,7 +49,8 @@ struct Tc2Args {
     unsigned int* ready;           // [nprod][kFlagStride]  ready[p][l] = t+1: Zbar_l (and A_{l-1}) of tile t are in memory
     unsigned int* done;            // [nprod][kFlagStride]  done[p][l]  = t+1: server has both operands of tile t on chip
     int nprod, q, zdepth;
-    long long* dbg;                // optional [8]: cycle counters of producer 0 (scripts/tc2_probe.py), or null
+    long long* dbg;                // optional [8]: cycle counters of producer 0 (PINN_TC2_DBG=1), or null
+    int* trap_site;                // mapped host memory [4]: {site, block, a, b} of a wait that timed out (see tc2::trap_at)
 };
 constexpr int kFlagStride = kMaxLayers + 2;
 
@@ -58,7 +59,7 @@ namespace tc2 {
 constexpr int T = 21, G = 4, NGRP = 6;     // points per tile, per group; groups per tile (the last holds one point)
 constexpr int OUTCOL = 256;                // TMEM columns of the output-layer accumulator
 // single-thread roles next to the epilogue work every thread does (one per warp, so their waits do not serialise)
-constexpr int kLoader = 32, kPublisher = 64, kWaiter = 96;
+constexpr int kLoader = 128, kPublisher = 64, kWaiter = 96;   // (the loader sits in a warp of M-tile 1: it sees the end of the whole step first)
 
 // tanh and s = 1 - tanh^2 from one exp2 and one reciprocal (absolute error ~2e-7; s keeps its RELATIVE accuracy
 // for saturated units, which 1 - a*a cannot).
@@ -78,17 +79,42 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// Bounded: a hand-off that has not happened after ~4e9 cycles (2 s; normal waits are microseconds) is a protocol
-// failure — trap, so the launch fails loudly instead of hanging the GPU.
-__device__ __forceinline__ void wait_ge(const unsigned* p, unsigned v) {
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// A protocol failure (a hand-off that never happens) must fail loudly, and say where: the wait site goes to mapped host
+// memory (it survives the trap), then the launch is killed.  pinn_last_error() reports it.
+__device__ long long g_wait_bound = 1LL << 30;      // cycles a hand-off may take (~0.5 s; PINN_TC2_TIMEOUT_SHIFT raises it for profilers)
+__device__ __noinline__ void trap_at(int* where, int site, int a, int b) {
+    if (where) {
+        where[1] = (int)blockIdx.x; where[2] = a; where[3] = b;
+        __threadfence_system();
+        where[0] = site;
+        __threadfence_system();
+    }
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait_at(uint64_t* bar, uint32_t parity, int* where, int site) {
+    const uint32_t addr = umma::smem_u32(bar);
+    uint32_t done, polls = 0;
+    long long t0 = 0;
+    do {
+        // (suspend-time hint: the warp sleeps in hardware until the phase completes or ~10 us pass — far fewer issue slots taken
+        //  from the warps that are computing than a tight poll)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity), "r"(10000u) : "memory");
+        if (!done && (++polls & 63u) == 0u) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > g_wait_bound) trap_at(where, site, (int)parity, 0);
+        }
+    } while (!done);
+}
+__device__ __forceinline__ void wait_ge_at(const unsigned* p, unsigned v, int* where, int site) {
     if (ld_acquire(p) >= v) return;
     const long long t0 = clock64();
     while (ld_acquire(p) < v) {
         __nanosleep(64);
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if (clock64() - t0 > 4 * g_wait_bound) trap_at(where, site, (int)v, (int)ld_acquire(p));
     }
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
 }
@@ -125,6 +151,28 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
     #pragma unroll
     for (int i = 0; i < 4; i++) v[i] = __uint_as_float(r[i]);
 }
+// ---- small TMEM stores / loads: operand words parked in the accumulator columns their own thread has just consumed ----
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait12(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]) :: "memory");
+}
+__device__ __forceinline__ void tmem_wait4(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) :: "memory");
+}
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
@@ -160,7 +208,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     constexpr uint32_t CHS = (uint32_t)H * 16u;         // byte stride between n-chunks of an operand image
     extern __shared__ __align__(128) uint8_t smem2_raw[];
     uint8_t* const smem = smem2_raw;
-    __shared__ uint64_t wbar[2], mma_bar, out_bar, slab_free, full_bar[3], empty_bar[3], fin_bar;
+    __shared__ uint64_t wbar[2], mma_bar, m0_bar, out_bar, slab_free, full_bar[3], empty_bar[3], fin_bar;
     __shared__ uint32_t tmem_slot;
 
     const int L = nd.L;
@@ -168,11 +216,13 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     const int q4 = warp & 3, mt = (warp >> 2) % MT, half = (warp >> 2) / MT;
     const int j = mt * 128 + q4 * 32 + lane;            // the unit (TMEM lane q4*32 + lane of M-tile mt) this thread owns
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    // the UMMA issue blocks its thread for most of the step: it lives in a warp of the LAST M-tile, which waits for the end of the step anyway
+    const int kIssuer = MT == 2 ? 160 : 0;
 
     if (warp == 0) umma::tmem_alloc(&tmem_slot, 512u);
     if (tid == 0) {
         umma::mbar_init(&wbar[0], 1); umma::mbar_init(&wbar[1], 1);
-        umma::mbar_init(&mma_bar, 2); umma::mbar_init(&out_bar, 1); umma::mbar_init(&fin_bar, 1); umma::mbar_init(&slab_free, 1);
+        umma::mbar_init(&mma_bar, 2); umma::mbar_init(&m0_bar, 2); umma::mbar_init(&out_bar, 1); umma::mbar_init(&fin_bar, 1); umma::mbar_init(&slab_free, 1);
         for (int i = 0; i < 3; i++) { umma::mbar_init(&full_bar[i], 1); umma::mbar_init(&empty_bar[i], 1); }
         umma::mbar_fence_init();
     }
@@ -198,14 +248,15 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
                 for (int p = i0; p < P; p += ta.q) {
                     if (t >= tiles_of_producer(ntiles, p, P)) continue;
                     any = true;
-                    wait_ge(ta.ready + (size_t)p * kFlagStride + l, (unsigned)t + 1u);
+                    wait_ge_at(ta.ready + (size_t)p * kFlagStride + l, (unsigned)t + 1u, ta.trap_site, 111);
                     fence_proxy_async_all();
                     const unsigned item = (unsigned)t * (unsigned)(L - 1) + (unsigned)(L - l);
-                    const uint8_t* srcA = ta.stash_a + ((size_t)p * L + (l - 2)) * OPB;          // A_{l-1}
+                    // A_{l-1}; A_1 has two copies (tile parity; the second one in the unused slot of A_L), see the producer
+                    const uint8_t* srcA = ta.stash_a + ((size_t)p * L + ((l == 2 && (t & 1)) ? L - 1 : l - 2)) * OPB;
                     const uint8_t* srcZ = ta.zring + ((size_t)p * ta.zdepth + item % (unsigned)ta.zdepth) * OPB;
                     for (int h = 0; h < 2; h++, it++) {
                         const unsigned st = it % 3u;
-                        if (it >= 3u) umma::mbar_wait(&empty_bar[st], ((it / 3u) - 1u) & 1u);
+                        if (it >= 3u) mbar_wait_at(&empty_bar[st], ((it / 3u) - 1u) & 1u, ta.trap_site, 101);
                         umma::mbar_expect_tx(&full_bar[st], 2 * HALF);
                         umma::bulk_g2s(smem + (size_t)st * OPB, srcA + (size_t)h * HALF, HALF, &full_bar[st]);
                         umma::bulk_g2s(smem + (size_t)st * OPB + HALF, srcZ + (size_t)h * HALF, HALF, &full_bar[st]);
@@ -222,7 +273,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
                     any = true;
                     for (int h = 0; h < 2; h++, it++) {
                         const unsigned st = it % 3u;
-                        umma::mbar_wait(&full_bar[st], (it / 3u) & 1u);
+                        mbar_wait_at(&full_bar[st], (it / 3u) & 1u, ta.trap_site, 102);
                         umma::tc_fence_after();
                         const uint32_t sa = umma::smem_u32(smem + (size_t)st * OPB), sz = sa + HALF;
                         // both operands K-major over n: 8-column chunks CHS apart, 8 rows (units) 128 B apart
@@ -238,7 +289,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
             }
             umma::mma_commit(&fin_bar);
         }
-        umma::mbar_wait(&fin_bar, 0);
+        mbar_wait_at(&fin_bar, 0, ta.trap_site, 103);
         umma::tc_fence_after();
         if (any_work) {                                 // drain: lane = fan-in unit k, columns = units j
             float* dst = part + nd.offW[l] + (size_t)j * H;
@@ -311,11 +362,11 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     };
     auto wait_step = [&](long long s_) {
         #pragma unroll
-        for (int m = 0; m < MT; m++) umma::mbar_wait(&wbar[slab_buf(s_, m)], slab_phase(s_));
+        for (int m = 0; m < MT; m++) mbar_wait_at(&wbar[slab_buf(s_, m)], slab_phase(s_), ta.trap_site, 104);
     };
     long long sc = 0;
     uint32_t mma_phase = 0, out_phase = 0;
-    if (tid == 0) request_step(0);
+    if (tid == kIssuer) request_step(0);
     __syncthreads();
 
     // This thread: unit j, column groups g0..g0+2 (4 points = 24 columns = 3 operand chunks each).  Half 1 ends with the
@@ -331,15 +382,35 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     auto chunk_ok = [&](int g, int c) { return 3 * g + c < 16; };
     // 24 FP32 results of group g -> bf16 chunks of this unit's row of an operand image
     // (row: this unit's row of an image in shared memory; grow: the same row of its copy in global memory, or null)
-    auto store_group = [&](uint8_t* row, uint8_t* grow, int g, const float* out) {
+    // early = the second M-tile's UMMA is still reading the operand buffer (this warp started as soon as ITS M-tile was done):
+    // the chunks wait in TMEM — in this thread's own accumulator columns, already consumed — and move over afterwards
+    const uint32_t tm_hold = tmem + lane_addr + (uint32_t)(mt * 128 + 72 * half);
+    auto store_group = [&](uint8_t* row, uint8_t* grow, int g, const float* out, bool early = false) {
         #pragma unroll
         for (int c = 0; c < 3; c++)
             if (chunk_ok(g, c)) {
-                const uint4 w = make_uint4(pack2(out[8 * c], out[8 * c + 1]), pack2(out[8 * c + 2], out[8 * c + 3]),
-                                           pack2(out[8 * c + 4], out[8 * c + 5]), pack2(out[8 * c + 6], out[8 * c + 7]));
-                *reinterpret_cast<uint4*>(row + (size_t)(3 * g + c) * CHS) = w;
+                const uint32_t w4[4] = {pack2(out[8 * c], out[8 * c + 1]), pack2(out[8 * c + 2], out[8 * c + 3]),
+                                        pack2(out[8 * c + 4], out[8 * c + 5]), pack2(out[8 * c + 6], out[8 * c + 7])};
+                const uint4 w = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                if (early) tmem_st4(tm_hold + (uint32_t)(12 * (g - g0) + 4 * c), w4);
+                else *reinterpret_cast<uint4*>(row + (size_t)(3 * g + c) * CHS) = w;
                 if (grow) __stcg(reinterpret_cast<uint4*>(grow + (size_t)(3 * g + c) * CHS), w);
             }
+    };
+    // parked chunks -> operand buffer (after the UMMA that was reading it has completed)
+    auto unpark = [&]() {
+        tmem_st_wait();
+        #pragma unroll
+        for (int gi = 0; gi < 3; gi++) {
+            const int g = g0 + gi;
+            uint32_t w[12];
+            if (g < NGRP - 1) { tmem_ld8_nowait(tm_hold + (uint32_t)(12 * gi), w); tmem_ld4_nowait(tm_hold + (uint32_t)(12 * gi + 8), w + 8); tmem_wait12(w); }
+            else { tmem_ld4_nowait(tm_hold + (uint32_t)(12 * gi), w); tmem_wait4(w); }
+            #pragma unroll
+            for (int c = 0; c < 3; c++)
+                if (chunk_ok(g, c))
+                    *reinterpret_cast<uint4*>(op_row + (size_t)(3 * g + c) * CHS) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        }
     };
     auto unpack_chunk = [&](const uint4& w, float* v) {
         v[0] = bf_lo(w.x); v[1] = bf_hi(w.x); v[2] = bf_lo(w.y); v[3] = bf_hi(w.y);
@@ -353,6 +424,11 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
         tmem_wait24(r);
         #pragma unroll
         for (int i = 0; i < 24; i++) v[i] = __uint_as_float(r[i]);
+    };
+    // the same in two halves, so that the load of the next group is in flight while this one is worked on
+    auto acc_issue = [&](int g, uint32_t* r) {
+        tmem_ld16_nowait(tm_row + (uint32_t)(24 * g), r);
+        tmem_ld8_nowait(tm_row + (uint32_t)(24 * g + 16), r + 16);
     };
     // forward tanh layer on one point: z (value, 3 first, 2 second tangents) -> a, a', a'' ; returns s
     auto fwd_point = [&](const float* z, float bias, float* out) -> float {
@@ -386,12 +462,12 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
         return z0;
     };
     // forward epilogue of one group: pre-activations z (24) -> operand chunks (+ bf16 remainder image for layer L) + s stash
-    auto fwd_group = [&](int l, int g, const float* z, float bias, uint8_t* lo_row, uint8_t* grow) {
+    auto fwd_group = [&](int l, int g, const float* z, float bias, uint8_t* lo_row, uint8_t* grow, bool early = false) {
         float out[24], sv[4];
         #pragma unroll
         for (int pp = 0; pp < G; pp++) sv[pp] = fwd_point(z + NC * pp, bias, out + NC * pp);
         if (g == NGRP - 1) { out[6] = 0.0f; out[7] = 0.0f; }                 // pad columns 126, 127 of the tile
-        store_group(op_row, grow, g, out);
+        store_group(op_row, grow, g, out, early);
         if (lo_row) {
             float lo[24];
             #pragma unroll
@@ -411,7 +487,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
         const unsigned item = (unsigned)t_ * (unsigned)(L - 1) + (unsigned)(L - l);
         if (item >= (unsigned)ta.zdepth) {
             const unsigned old = item - (unsigned)ta.zdepth;
-            wait_ge(dn + (L - (int)(old % (unsigned)(L - 1))), old / (unsigned)(L - 1) + 1u);
+            wait_ge_at(dn + (L - (int)(old % (unsigned)(L - 1))), old / (unsigned)(L - 1) + 1u, ta.trap_site, 112);
         }
     };
     auto ring_row = [&](int t_, int l) -> uint8_t* {
@@ -423,7 +499,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     auto issue_step = [&](long long s_, bool fwd) {
         #pragma unroll
         for (int m = 0; m < MT; m++) {
-            umma::mbar_wait(&wbar[slab_buf(s_, m)], slab_phase(s_));
+            mbar_wait_at(&wbar[slab_buf(s_, m)], slab_phase(s_), ta.trap_site, 105);
             umma::tc_fence_after();
             if (fwd)       // A = W_l^T slab (MN-major: 8-unit groups CHS apart, 8 k rows 128 B apart)
                 umma::gemm_issue(tmem + (uint32_t)(m * 128), w_addr + (uint32_t)slab_buf(s_, m) * SLAB, 128, CHS, 256,
@@ -431,7 +507,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
             else           // A = W_l rows (K-major: 8-unit chunks of j 2048 B apart, 8 k rows 128 B apart)
                 umma::gemm_issue(tmem + (uint32_t)(m * 128), w_addr + (uint32_t)slab_buf(s_, m) * SLAB, 2048, 128, 4096,
                                  op_addr, 128, CHS, 256, umma::idesc_bf16(128, 128, 0, 1), H / 16, 0u);
-            if (MT == 2 && m == 0) umma::mma_commit(&slab_free);
+            if (MT == 2 && m == 0) { umma::mma_commit(&slab_free); umma::mma_commit(&m0_bar); }
         }
         umma::mma_commit(&mma_bar);
         if (MT == 1) request_step(s_ + 1);
@@ -439,7 +515,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     uint32_t free_phase = 0;                         // loader thread (tid 32), MT == 2
     // loader thread: next step's slab for buffer 0 as soon as M-tile 0 is done, for buffer 1 when the whole step is
     auto loader_first = [&](long long s_next) {
-        umma::mbar_wait(&slab_free, free_phase); free_phase ^= 1;
+        mbar_wait_at(&slab_free, free_phase, ta.trap_site, 106); free_phase ^= 1;
         if (s_next < nsteps) {
             umma::mbar_expect_tx(&wbar[0], SLAB);
             umma::bulk_g2s(Wb0, slab_src(s_next, 0), SLAB, &wbar[0]);
@@ -455,7 +531,11 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     for (int t = 0; t < my_tiles; t++) {
         const long long c_t0 = dbg ? clock64() : 0;
         const unsigned long long base = (unsigned long long)(p + (long long)t * P) * T;
-        if (tid == kWaiter && t > 0) wait_ge(dn + 2, (unsigned)t);   // A_1 of the previous tile has been streamed by server 2
+        // A_1 is the first image a tile writes and the last one its dW server reads (dW_2 closes the reverse pass): with one copy
+        // the next tile would wait for that server at once, so A_1 alternates between two copies (the slot of A_L is free: A_L is
+        // never stashed) and a tile only waits for the tile before the previous one
+        if (tid == kWaiter && t > 1) wait_ge_at(dn + 2, (unsigned)t - 1u, ta.trap_site, 113);
+        const size_t a1_off = (t & 1) ? (size_t)(L - 1) * OPB : 0;
         if (tid < T * DIN) {
             const int pt = tid / DIN, k = tid - pt * DIN;
             xs[pt * 4 + k] = (base + pt < ta.set.n) ? __ldg(ta.set.x + (base + pt) * DIN + k) : 0.0f;
@@ -481,7 +561,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
                     #pragma unroll
                     for (int i = 0; i < N2; i++) z[NC * pp + 1 + DIN + i] = 0.0f;
                 }
-                fwd_group(1, g, z, b1, nullptr, stA + (size_t)j * 16);
+                fwd_group(1, g, z, b1, nullptr, stA + a1_off + (size_t)j * 16);
             }
         }
         umma::fence_async_smem();
@@ -493,26 +573,45 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
         uint8_t* lo_img = Wb0;                       // bf16 remainder of A_L: in a weight buffer that is idle around the output layer
         for (int l = 2; l <= L; l++, sc++) {
             const long long c_a = dbg ? clock64() : 0;
-            if (tid == 0) issue_step(sc, true);
+            if (tid == kIssuer) issue_step(sc, true);
             if (tid == kWaiter) {
-                if (l < L && t > 0) wait_ge(dn + (l + 1), (unsigned)t);   // A_l of the previous tile may be overwritten
+                if (l < L && t > 0) wait_ge_at(dn + (l + 1), (unsigned)t, ta.trap_site, 114);   // A_l of the previous tile may be overwritten
+                if (MT == 2) mbar_arrive(&m0_bar);
                 mbar_arrive(&mma_bar);
             }
             if (MT == 2 && tid == kLoader && l < L) loader_first(sc + 1);
-            if (MT == 2 && tid == kLoader && l == L) { umma::mbar_wait(&slab_free, free_phase); free_phase ^= 1; }
+            if (MT == 2 && tid == kLoader && l == L) { mbar_wait_at(&slab_free, free_phase, ta.trap_site, 107); free_phase ^= 1; }
             const float bl = __ldg(ta.params + nd.offB[l] + j);
-            umma::mbar_wait(&mma_bar, mma_phase); mma_phase ^= 1;
+            // the warps of M-tile 0 start their epilogue as soon as ITS UMMAs are done, under the UMMAs of M-tile 1
+            const bool early = MT == 2 && mt == 0;
+            if (early) { mbar_wait_at(&m0_bar, mma_phase, ta.trap_site, 115); }
+            else {
+                mbar_wait_at(&mma_bar, mma_phase, ta.trap_site, 108);
+                if (MT == 2 && tid == kLoader && l < L) loader_second(sc + 1);
+            }
             umma::tc_fence_after();
-            if (MT == 2 && tid == kLoader && l < L) loader_second(sc + 1);
             if (l == L) lo_img = Wb0 + (MT == 2 ? 0 : (size_t)(sc & 1) * SLAB);
             const long long c_b = dbg ? clock64() : 0;
-            #pragma unroll
-            for (int gi = 0; gi < 3; gi++) {
-                float z[24];
-                load_acc(g0 + gi, z);
-                fwd_group(l, g0 + gi, z, bl, l == L ? lo_img + (size_t)j * 16 : nullptr,
-                          l < L ? stA + (size_t)(l - 1) * OPB + (size_t)j * 16 : nullptr);
+            {
+                uint32_t rz[2][24];
+                acc_issue(g0, rz[0]);
+                #pragma unroll
+                for (int gi = 0; gi < 3; gi++) {
+                    tmem_wait24(rz[gi & 1]);
+                    if (gi < 2) acc_issue(g0 + gi + 1, rz[(gi + 1) & 1]);
+                    float z[24];
+                    #pragma unroll
+                    for (int i = 0; i < 24; i++) z[i] = __uint_as_float(rz[gi & 1][i]);
+                    fwd_group(l, g0 + gi, z, bl, l == L ? lo_img + (size_t)j * 16 : nullptr,
+                              l < L ? stA + (size_t)(l - 1) * OPB + (size_t)j * 16 : nullptr, early);
+                }
             }
+            if (early) {
+                mbar_wait_at(&mma_bar, mma_phase, ta.trap_site, 116);
+                umma::tc_fence_after();
+                unpark();
+            }
+            mma_phase ^= 1;
             umma::fence_async_smem();
             umma::tc_fence_before();
             __syncthreads();
@@ -521,7 +620,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
 
         // ---------------- output layer on the tensor cores: y[n, :] = (A_L hi + lo)^T[n, k] . [W_{L+1} hi | lo][k, :] ----------------
         const long long c_o = dbg ? clock64() : 0;
-        if (tid == 0) {
+        if (tid == kIssuer) {
             umma::tc_fence_after();
             umma::gemm_issue(tmem + OUTCOL, op_addr, 128, CHS, 256, umma::smem_u32(wo16), 128, CHS, 256,
                              umma::idesc_bf16(128, 16, 1, 1), H / 16, 0u);
@@ -529,7 +628,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
                              umma::idesc_bf16(128, 16, 1, 1), H / 16, 1u);
             umma::mma_commit(&out_bar);
         }
-        umma::mbar_wait(&out_bar, out_phase); out_phase ^= 1;
+        mbar_wait_at(&out_bar, out_phase, ta.trap_site, 109); out_phase ^= 1;
         umma::tc_fence_after();
         if (MT == 2 && tid == kLoader) { loader_second(sc); if (sc < nsteps) { umma::mbar_expect_tx(&wbar[0], SLAB); umma::bulk_g2s(Wb0, slab_src(sc, 0), SLAB, &wbar[0]); } }
         if (warp < 4) {                              // lane n = column n of the tile
@@ -584,7 +683,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
                 for (int c = 0; c < 3; c++) {
                     pa[gi][c] = make_uint4(0u, 0u, 0u, 0u);
                     if (chunk_ok(g, c)) {
-                        if (l < L) pa[gi][c] = __ldcg(reinterpret_cast<const uint4*>(stA + (size_t)(l - 1) * OPB + (size_t)(3 * g + c) * CHS + (size_t)j * 16));
+                        if (l < L) pa[gi][c] = __ldcg(reinterpret_cast<const uint4*>(stA + (l == 1 ? a1_off : (size_t)(l - 1) * OPB) + (size_t)(3 * g + c) * CHS + (size_t)j * 16));
                         else pa[gi][c] = *reinterpret_cast<const uint4*>(op_row + (size_t)(3 * g + c) * CHS);   // A_L is still the operand image
                     }
                 }
@@ -593,11 +692,15 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
         prefetch_stash(L);
         for (int l = L; l >= 1; l--) {
             const long long c_d = dbg ? clock64() : 0;
+            const bool early = MT == 2 && mt == 0 && l < L;      // (see the forward pass)
             if (l < L) {
                 if (MT == 2 && tid == kLoader) loader_first(sc);
-                umma::mbar_wait(&mma_bar, mma_phase); mma_phase ^= 1;
+                if (early) { mbar_wait_at(&m0_bar, mma_phase, ta.trap_site, 117); }
+                else {
+                    mbar_wait_at(&mma_bar, mma_phase, ta.trap_site, 110);
+                    if (MT == 2 && tid == kLoader) loader_second(sc);
+                }
                 umma::tc_fence_after();
-                if (MT == 2 && tid == kLoader) loader_second(sc);
             }
             const long long c_e = dbg ? clock64() : 0;
             float dbsum = 0.0f, dw1[DIN] = {0.0f, 0.0f, 0.0f};
@@ -637,7 +740,15 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
                     }
                 }
                 if (g == NGRP - 1) { zb[6] = 0.0f; zb[7] = 0.0f; }
-                if (l > 1) store_group(op_row, zrow, g, zb);
+                if (l > 1) store_group(op_row, zrow, g, zb, early);
+            }
+            if (l < L) {
+                if (early) {
+                    mbar_wait_at(&mma_bar, mma_phase, ta.trap_site, 118);
+                    umma::tc_fence_after();
+                    if (l > 1) unpark();
+                }
+                mma_phase ^= 1;
             }
             dbs[(size_t)(half * L + (l - 1)) * H + j] += dbsum;
             if (l == 1) {
@@ -651,13 +762,14 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
             umma::tc_fence_before();
             __syncthreads();
             const long long c_f = dbg ? clock64() : 0;
-            if (tid == 0) issue_step(sc, false);
+            if (tid == kIssuer) issue_step(sc, false);
             if (tid == kPublisher) {                     // Zbar_l (and, since the forward pass, A_{l-1}) are in memory
                 __threadfence();
                 st_release(rdy + l, (unsigned)t + 1u);
             }
             if (tid == kWaiter) {
                 if (l > 2) ring_wait(t, l - 1);          // ring slot of Zbar_{l-1}, written by the next epilogue
+                if (MT == 2) mbar_arrive(&m0_bar);
                 mbar_arrive(&mma_bar);
             }
             sc++;
