@@ -56,8 +56,9 @@ ABI_SYMBOLS = [
     "pinn_config_default", "pinn_num_channels", "pinn_num_params", "pinn_shard_range",
     "pinn_create", "pinn_destroy", "pinn_last_error",
     "pinn_set_params", "pinn_get_params", "pinn_get_grads", "pinn_get_optimizer", "pinn_set_optimizer",
-    "pinn_sample_points", "pinn_resample_points", "pinn_set_points", "pinn_get_points", "pinn_local_count",
-    "pinn_train_step", "pinn_train_step_host", "pinn_train_steps", "pinn_loss_grad",
+    "pinn_sample_points", "pinn_resample_points", "pinn_set_points", "pinn_set_points_device", "pinn_set_points_view",
+    "pinn_h2d_point_bytes", "pinn_get_points", "pinn_local_count",
+    "pinn_train_step", "pinn_train_step_host", "pinn_train_step_device", "pinn_train_steps", "pinn_loss_grad",
     "pinn_forward", "pinn_residual", "pinn_synchronize",
     "pinn_save", "pinn_load", "pinn_exact_solution", "pinn_evaluate",
     "pinn_comm_unique_id", "pinn_comm_init", "pinn_comm_p2p_export", "pinn_comm_p2p_open", "pinn_step_local", "pinn_step_apply",
@@ -100,6 +101,10 @@ def lib():
     L.pinn_sample_points.argtypes = [vp]
     L.pinn_resample_points.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64]
     L.pinn_set_points.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.pinn_set_points_device.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.pinn_set_points_view.argtypes = [vp, C.c_int, vp]
+    L.pinn_h2d_point_bytes.argtypes = [vp]; L.pinn_h2d_point_bytes.restype = C.c_ulonglong
+    L.pinn_train_step_device.argtypes = [vp, vp, C.c_size_t, P(PinnStepOut)]
     L.pinn_get_points.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.pinn_local_count.argtypes = [vp, C.c_int]; L.pinn_local_count.restype = C.c_size_t
     L.pinn_train_step.argtypes = [vp, P(PinnStepOut)]
@@ -239,6 +244,27 @@ class Network:
     def set_points(self, which, x):
         x = np.ascontiguousarray(x, dtype=np.float32)
         self._check(self._L.pinn_set_points(self._h, which, _ptr(x), len(x)))
+
+    def set_points_device(self, which, d_ptr, n):
+        """d_ptr: integer DEVICE address of [n, d_in] float32 points on this handle's GPU (device-to-device, no H2D)."""
+        self._check(self._L.pinn_set_points_device(self._h, which, C.c_void_p(d_ptr), n))
+
+    def set_points_view(self, which, d_ptr, n_floats, transposed=False):
+        """Builds the reference's 48-byte kernel-argument view device::tensor::variables<float> around a device buffer
+        (variables.cuh:6-52: data @0, shape @8, stride @16, dim @24, n @32, transposed @40) and hands it over."""
+        import struct
+        v = struct.pack("<QQQQQ?7x", d_ptr, 0, 0, 2, n_floats, bool(transposed))
+        assert len(v) == 48
+        buf = C.create_string_buffer(v, 48)
+        self._check(self._L.pinn_set_points_view(self._h, which, buf))
+
+    def h2d_point_bytes(self):
+        return int(self._L.pinn_h2d_point_bytes(self._h))
+
+    def train_step_device(self, d_ptr, n):
+        o = PinnStepOut()
+        self._check(self._L.pinn_train_step_device(self._h, C.c_void_p(d_ptr), n, C.byref(o)))
+        return self._out(o)
 
     # -- hot path
     @staticmethod

@@ -278,9 +278,11 @@ reduce_exchange_adam_kernel(const NetDims nd, const AdamArgs a, float* __restric
                             float* __restrict__ loss_out, int* __restrict__ flag, const P2PArgs x, const FragMirror fm, float* hrec,
                             double* __restrict__ beta_pow) {
     __shared__ float part[32][33];
+    __shared__ int peer_missing;
     constexpr int RU = 8;
     const int PP = nd.PP, n_out = nd.P + 3;
     const int col = blockIdx.x * 32 + threadIdx.x;
+    if (threadIdx.x == 0 && threadIdx.y == 0) peer_missing = 0;
     float s = 0.0f;
     if (col < n_out) {
         auto sum_rows = [&](const float* __restrict__ base, int rows) {
@@ -325,12 +327,22 @@ reduce_exchange_adam_kernel(const NetDims nd, const AdamArgs a, float* __restric
         const unsigned long long* my_flags = reinterpret_cast<const unsigned long long*>(x.peers[x.rank]);
         for (int r = 0; r < x.nranks; r++) {                           // poll LOCAL memory only
             while (ld_acquire_sys(my_flags + r) < x.seq) {
-                if (clock64() - t0 > 4000000000LL) { *x.err_flag = PINN_ERR_NCCL; break; }   // ~2 s: a peer never arrived
+                if (clock64() - t0 > 4000000000LL) { *x.err_flag = PINN_ERR_NCCL; peer_missing = 1; break; }   // ~2 s: a peer never arrived
                 __nanosleep(100);
             }
         }
     }
     __syncthreads();
+    // a peer that never arrived: its slot holds an old step — do NOT apply Adam to an incomplete sum (the ranks would drift
+    // apart silently); the flag reaches the caller through the step record (pinn_train_step returns PINN_ERR_NCCL)
+    if (peer_missing) {
+        if (threadIdx.y == 0 && col == nd.P && hrec) {
+            const float fs = __uint_as_float((unsigned int)tstep);
+            reinterpret_cast<float4*>(hrec)[0] = make_float4(0.0f, 0.0f, 0.0f, fs);
+            reinterpret_cast<float4*>(hrec)[1] = make_float4(0.0f, __int_as_float(PINN_ERR_NCCL), fs, 0.0f);
+        }
+        return;
+    }
     if (threadIdx.y == 0 && col < n_out) {
         const float* mine = x.peers[x.rank] + kXchgHeader;
         float g = 0.0f;
@@ -473,6 +485,7 @@ struct pinn_ctx {
     double kernel_ms = 0.0; uint64_t kernel_count = 0, launches = 0;
     int last_grid = 0, rows_a = 0, rows_b = 0;        // partial rows the last interior / boundary launches used
     uint64_t host_step = 0;
+    unsigned long long h2d_point_bytes = 0;            // host->device bytes this handle has copied for point sets
 };
 
 static int fail(pinn_ctx* c, int code, const std::string& msg) {
@@ -486,6 +499,14 @@ static int fail(pinn_ctx* c, int code, const std::string& msg) {
     } else g_create_error = msg;
     return code;
 }
+// A handle created with nranks > 1 holds a SHARD: without a communicator its sums are local yet scaled by the global counts.
+static int need_comm(pinn_ctx* c, const char* fn) {
+    if (c->cfg.nranks > 1 && !c->comm)
+        return fail(c, PINN_ERR_INVALID_ARGUMENT, std::string(fn) + ": nranks > 1 but no communicator (pinn_comm_init), or drive the "
+                    "collective yourself with pinn_step_local / pinn_grad_buffer / pinn_step_apply");
+    return PINN_OK;
+}
+
 #define CUDA_TRY(c, fn, call)                                                                         \
     do { cudaError_t e_ = (call);                                                                     \
          if (e_ != cudaSuccess) return fail((c), PINN_ERR_CUDA, std::string(fn) + ": " + #call + " -> " + \
@@ -1091,6 +1112,17 @@ static int step_once(pinn_ctx* c) {
     return rc;
 }
 
+// Device error channel (reference include/device/runtime.cuh:8-48: a device-side code read back by the host and thrown as
+// device_exception{code, name}): ANY non-zero flag the step tail left is returned and cleared — not only the overflow code.
+static int device_flag_error(pinn_ctx* c, int flag) {
+    cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream);
+    if (flag == PINN_ERR_DEVICE_OVERFLOW)
+        return fail(c, PINN_ERR_DEVICE_OVERFLOW, "network::train_step: overflow");   // reference runtime.cuh:17-38 text
+    if (flag == PINN_ERR_NCCL)
+        return fail(c, PINN_ERR_NCCL, "network::train_step: a peer rank never arrived at the gradient exchange (step not applied)");
+    return fail(c, flag, "network::train_step: device error " + std::to_string(flag));
+}
+
 static int read_out(pinn_ctx* c, pinn_step_out* out) {
     if (!out) return PINN_OK;
     float* hp = c->h_pinned + 8;                          // copy-path scratch (the first 8 floats are the mapped step record)
@@ -1100,11 +1132,7 @@ static int read_out(pinn_ctx* c, pinn_step_out* out) {
     out->mse_boundary = hp[2]; out->mse_initial = hp[3];
     out->step = c->host_step;
     int flag; memcpy(&flag, hp + 4, sizeof(int));
-    if (flag == PINN_ERR_DEVICE_OVERFLOW) {
-        cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream);
-        return fail(c, PINN_ERR_DEVICE_OVERFLOW, "network::train_step: overflow");   // reference runtime.cuh:17-38 text
-    }
-    return PINN_OK;
+    return flag ? device_flag_error(c, flag) : PINN_OK;
 }
 
 // Result of the latest TRAINING step without a copy or a stream synchronisation: the step tail wrote the loss record and,
@@ -1130,11 +1158,7 @@ static int read_step(pinn_ctx* c, pinn_step_out* out) {
     out->loss = h[0]; out->mse_residual = h[1]; out->mse_boundary = h[2]; out->mse_initial = h[4];
     out->step = c->host_step;
     const int flag = (int)w[5];
-    if (flag == PINN_ERR_DEVICE_OVERFLOW) {
-        cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream);
-        return fail(c, PINN_ERR_DEVICE_OVERFLOW, "network::train_step: overflow");   // reference runtime.cuh:17-38 text
-    }
-    return PINN_OK;
+    return flag ? device_flag_error(c, flag) : PINN_OK;
 }
 
 static void drain_profile(pinn_ctx* c) {
@@ -1374,9 +1398,50 @@ int pinn_set_points(pinn_ctx* c, int set, const float* x, size_t n) {
     if (n > c->cap[set]) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_set_points: more points than the shard fixed at create time");
     CUDA_TRY(c, "pinn_set_points", cudaSetDevice(c->cfg.device));
     if (n) CUDA_TRY(c, "pinn_set_points", cudaMemcpyAsync(c->d_x[set], x, n * c->nd.d_in * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    c->h2d_point_bytes += n * c->nd.d_in * sizeof(float);
     c->n_local[set] = n;
     return PINN_OK;
 }
+
+// Points that already live on this device — the device half of a reference tensor<float> (interface<T>::d_var().data,
+// include/device/interface.cuh:248-249) or any other device buffer: device-to-device, no host round trip.
+int pinn_set_points_device(pinn_ctx* c, int set, const float* d_x, size_t n) {
+    if (!c || set < 0 || set > 2 || (!d_x && n)) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_set_points_device: invalid argument");
+    if (n > c->cap[set]) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_set_points_device: more points than the shard fixed at create time");
+    CUDA_TRY(c, "pinn_set_points_device", cudaSetDevice(c->cfg.device));
+    if (n) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, d_x) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != c->cfg.device) {
+            cudaGetLastError();
+            return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_set_points_device: not a device pointer of this handle's GPU (host memory goes through pinn_set_points)");
+        }
+        CUDA_TRY(c, "pinn_set_points_device", cudaMemcpyAsync(c->d_x[set], d_x, n * c->nd.d_in * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    c->n_local[set] = n;
+    return PINN_OK;
+}
+
+// The same from the reference's kernel-argument view device::tensor::variables<float> (include/device/variables.cuh:6-52):
+// a 48-byte POD passed BY VALUE to every reference kernel — {T* data @0, size_t* shape @8, size_t* stride @16, size_t dim @24,
+// size_t n @32, bool transposed @40}.  Accepts a [n_points, d_in] or flat view whose n is a multiple of d_in.
+int pinn_set_points_view(pinn_ctx* c, int set, const void* variables48) {
+    if (!c || !variables48) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_set_points_view: null argument");
+    struct View { const float* data; const size_t* shape; const size_t* stride; size_t dim, n; bool transposed; };
+    static_assert(sizeof(View) == 48, "device::tensor::variables<float> is 48 bytes");
+    View v; memcpy(&v, variables48, sizeof(v));
+    if (v.transposed) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_set_points_view: transposed views are not contiguous point lists");
+    if (v.n % (size_t)c->nd.d_in) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_set_points_view: size mismatch - " + std::to_string(v.n) + " is not a multiple of d_in");
+    return pinn_set_points_device(c, set, v.data, v.n / (size_t)c->nd.d_in);
+}
+
+int pinn_train_step_device(pinn_ctx* c, const float* d_x_interior, size_t n, pinn_step_out* out) {
+    if (!c) return PINN_ERR_INVALID_ARGUMENT;
+    if (int rcn = need_comm(c, "pinn_train_step_device")) return rcn;
+    const int rc = pinn_set_points_device(c, PINN_SET_INTERIOR, d_x_interior, n);
+    return rc ? rc : pinn_train_step(c, out);
+}
+
+unsigned long long pinn_h2d_point_bytes(const pinn_ctx* c) { return c ? c->h2d_point_bytes : 0ull; }
 
 int pinn_get_points(pinn_ctx* c, int set, float* x, size_t n) {
     if (!c || set < 0 || set > 2 || (!x && n)) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_get_points: invalid argument");
@@ -1411,6 +1476,7 @@ int pinn_step_apply(pinn_ctx* c, pinn_step_out* out) {
 
 int pinn_train_step(pinn_ctx* c, pinn_step_out* out) {
     if (!c) return PINN_ERR_INVALID_ARGUMENT;
+    if (int rcn = need_comm(c, "pinn_train_step")) return rcn;
     CUDA_TRY(c, "pinn_train_step", cudaSetDevice(c->cfg.device));
     int rc = step_once(c);
     if (!rc) rc = read_step(c, out);
@@ -1419,6 +1485,7 @@ int pinn_train_step(pinn_ctx* c, pinn_step_out* out) {
 
 int pinn_train_steps(pinn_ctx* c, int k, pinn_step_out* out) {
     if (!c || k < 1) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_train_steps: k must be >= 1");
+    if (int rcn = need_comm(c, "pinn_train_steps")) return rcn;
     CUDA_TRY(c, "pinn_train_steps", cudaSetDevice(c->cfg.device));
     for (int s = 0; s < k; s++) {
         const int rc = step_once(c);
@@ -1429,6 +1496,7 @@ int pinn_train_steps(pinn_ctx* c, int k, pinn_step_out* out) {
 
 int pinn_train_step_host(pinn_ctx* c, const float* x_interior, size_t n, pinn_step_out* out) {
     if (!c) return PINN_ERR_INVALID_ARGUMENT;
+    if (int rcn = need_comm(c, "pinn_train_step_host")) return rcn;
     // Width-20 mma kernel + pinned caller memory + a caller that waits for the result: no copy operation at all — the kernel
     // reads the points straight from the mapped host buffer (one 128-byte PCIe read per 16-point tile, hidden behind the
     // tile's own work) and leaves the resident copy in HBM behind for pinn_get_points / later steps.
@@ -1546,9 +1614,16 @@ int pinn_load(pinn_ctx* c, const char* path) {
     if (fread(w.data(), sizeof(float), P, f.get()) != P || fread(m.data(), sizeof(float), P, f.get()) != P ||
         fread(v.data(), sizeof(float), P, f.get()) != P)
         return fail(c, PINN_ERR_INVALID_ARGUMENT, std::string("pinn_load: truncated checkpoint - ") + path);
-    int rc = pinn_set_params(c, w.data(), P, 0);
+    // both uploads are validated before either mutates the handle ("left untouched" on failure): sizes match by the header
+    // check above; what can still fail is a CUDA call, after which the handle is unusable anyway
+    std::vector<float> w_old(P);
+    int rc = pinn_get_params(c, w_old.data(), P);
     if (rc) return rc;
-    return pinn_set_optimizer(c, m.data(), v.data(), P, h.step);
+    rc = pinn_set_params(c, w.data(), P, 0);
+    if (rc) return rc;
+    rc = pinn_set_optimizer(c, m.data(), v.data(), P, h.step);
+    if (rc) pinn_set_params(c, w_old.data(), P, 0);      // roll the parameters back: the handle is as it was
+    return rc;
 }
 
 int pinn_exact_solution(const pinn_config* cfg, const float* x, float* u, size_t n) {
@@ -1672,6 +1747,14 @@ int pinn_comm_p2p_open(pinn_ctx* c, const void* handles, int count) {
     if (!c || !handles) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_comm_p2p_open: null argument");
     if (count != c->cfg.nranks || !c->d_xchg) return fail(c, PINN_ERR_INVALID_ARGUMENT, "pinn_comm_p2p_open: need one handle per rank, after pinn_comm_p2p_export");
     CUDA_TRY(c, "pinn_comm_p2p_open", cudaSetDevice(c->cfg.device));
+    {   // every block of the exchange kernel waits for the last block of its own rank: all of them must be resident at once
+        int occ = 0;
+        CUDA_TRY(c, "pinn_comm_p2p_open", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reduce_exchange_adam_kernel, 1024, 0));
+        const int blocks = (c->nd.P + 3 + 31) / 32;
+        if (blocks > occ * c->num_sms)
+            return fail(c, PINN_ERR_UNSUPPORTED, "pinn_comm_p2p_open: the fused exchange kernel needs " + std::to_string(blocks) +
+                        " co-resident blocks, this GPU holds " + std::to_string(occ * c->num_sms) + " (use the NCCL collective for this network)");
+    }
     for (int r = 0; r < count; r++) {
         if (r == c->cfg.rank) { c->peer_ptr[r] = c->d_xchg; continue; }
         cudaIpcMemHandle_t h;

@@ -16,6 +16,7 @@
 //   for (int i = 0; i < 1000; i++) auto s = net.train_step();
 //   tensor<float> u = net.forward(points);
 
+#include<array>
 #include<string>
 #include<vector>
 #include<memory>
@@ -51,6 +52,32 @@ struct step_result {
 };
 
 enum class point_set: int { interior = PINN_SET_INTERIOR, boundary = PINN_SET_BOUNDARY, initial = PINN_SET_INITIAL };
+
+// One affine map of the network and what follows it — the "layer interface" of README.md:53.  A view: it borrows the
+// network's host mirrors (refreshed lazily from the GPU), it owns nothing, and it stays valid as long as the network does.
+//   z = a_prev . weight + bias   (weight is [fan_in, fan_out], row-major: the reference matmul layout, kernel.cuh:68-83;
+//   a = tanh(z) for the hidden layers, a = z for the output layer   bias adds by suffix broadcast, kernel.cuh:10-17)
+template<arithmetic T>
+class layer {
+    private:
+        const tensor<T> *w = nullptr;
+        const tensor<T> *b = nullptr;
+        size_t l = 0;
+        bool is_output = false;
+
+    public:
+        layer(const tensor<T> &weight, const tensor<T> &bias, size_t index, bool output) noexcept
+        :w{&weight}, b{&bias}, l{index}, is_output{output} {}
+
+        [[nodiscard]] inline const tensor<T> &weight(void) const noexcept { return *this->w; }
+        [[nodiscard]] inline const tensor<T> &bias(void) const noexcept { return *this->b; }
+        [[nodiscard]] inline size_t index(void) const noexcept { return this->l; }
+        [[nodiscard]] inline size_t fan_in(void) const noexcept { return this->w->get_shape()[0]; }
+        [[nodiscard]] inline size_t fan_out(void) const noexcept { return this->w->get_shape()[1]; }
+        [[nodiscard]] inline size_t size(void) const noexcept { return this->w->size() + this->b->size(); }
+        [[nodiscard]] inline bool output(void) const noexcept { return this->is_output; }
+        [[nodiscard]] inline const char *activation(void) const noexcept { return this->is_output? "identity": "tanh"; }
+};
 
 template<arithmetic T>
 class network {
@@ -159,6 +186,13 @@ class network {
             return *this->biases[l];
         }
 
+        // Layer l (0 = the input layer, layers() - 1 = the linear output layer) as a view on the host mirrors.
+        [[nodiscard]] layer<T> at(size_t l) const {
+            if (l >= this->weights.size()) throw std::out_of_range{"network::at: layer out of range"};
+            this->sync_host();
+            return layer<T>{*this->weights[l], *this->biases[l], l, l + 1 == this->weights.size()};
+        }
+
         // Flattened parameters W1, b1, W2, b2, ... (row-major, the order of the gradient buffer).
         [[nodiscard]] tensor<T> parameters(void) const {
             tensor<T> flat(as_shape, {this->n_params});
@@ -195,12 +229,32 @@ class network {
             return x;
         }
 
+        // A tensor whose DEVICE half can be reached — a tensor type that offers d_var(), the kernel-argument view the
+        // reference's own ops pass to their kernels (interface.cuh:248-249, variables.cuh:6-52) — is bound device to device
+        // (no host round trip; the tensor flushes a pending host write first, tensor.cuh:72-82).  The reference's tensor<T>
+        // keeps that member private (tensor.cuh:19-20), so with the UNMODIFIED header the host copy is uploaded instead;
+        // INTEGRATION.md shows the one accessor a maintainer adds to get the device path.
         network &set_points(point_set set, const tensor<T> &x) {
             if (x.dim() != 2 || x.get_shape()[1] != static_cast<size_t>(this->cfg.d_in))
                 throw std::invalid_argument{"network::set_points: expected a [n, d_in] matrix"};
-            this->check(pinn_set_points(this->ctx, static_cast<int>(set), x.raw(), x.get_shape()[0]), "set_points");
+            if constexpr (requires { x.d_var(); }) {
+                const auto view = x.d_var();
+                static_assert(sizeof(view) == 48, "device::tensor::variables<T> is the 48-byte kernel-argument view");
+                this->check(pinn_set_points_view(this->ctx, static_cast<int>(set), &view), "set_points");
+            } else {
+                this->check(pinn_set_points(this->ctx, static_cast<int>(set), x.raw(), x.get_shape()[0]), "set_points");
+            }
             return *this;
         }
+
+        // Points that already live on this network's GPU, by raw device pointer ([n, d_in] row-major).
+        network &set_points(point_set set, const T *device_points, size_t n) {
+            this->check(pinn_set_points_device(this->ctx, static_cast<int>(set), device_points, n), "set_points");
+            return *this;
+        }
+
+        // Host->device bytes copied for point sets so far (0 as long as only the device entry points were used).
+        [[nodiscard]] inline size_t h2d_point_bytes(void) const noexcept { return static_cast<size_t>(pinn_h2d_point_bytes(this->ctx)); }
 
         // ---- the hot path ----
         step_result train_step(void) {
@@ -216,6 +270,14 @@ class network {
                 throw std::invalid_argument{"network::train_step: expected a [n, d_in] matrix"};
             pinn_step_out o{};
             this->check(pinn_train_step_host(this->ctx, x_interior.raw(), x_interior.get_shape()[0], &o), "train_step");
+            this->device_dirty = true;
+            return network::to_result(o);
+        }
+
+        // One step on interior points that already live on this network's GPU.
+        step_result train_step(const T *device_points, size_t n) {
+            pinn_step_out o{};
+            this->check(pinn_train_step_device(this->ctx, device_points, n, &o), "train_step");
             this->device_dirty = true;
             return network::to_result(o);
         }
@@ -263,6 +325,38 @@ class network {
             tensor<T> y(as_shape, {n, static_cast<size_t>(this->cfg.d_out), static_cast<size_t>(this->n_channels)});
             this->check(pinn_residual(this->ctx, x.raw(), &y[0], nullptr, n), "derivatives");
             return y;
+        }
+
+        // ---- data parallel over the GPUs of one box: one network per rank (config.rank / config.nranks), each on its shard of
+        // every point set; one all-reduce of the flat [P + 3] gradient per step, then the same Adam update on every rank ----
+        [[nodiscard]] inline int rank(void) const noexcept { return this->cfg.rank; }
+        [[nodiscard]] inline int ranks(void) const noexcept { return this->cfg.nranks; }
+
+        // Rank 0 creates the 128-byte id and sends it to the other ranks by any means; every rank then calls comm_init.
+        [[nodiscard]] static std::array<char, PINN_COMM_ID_BYTES> comm_id(void) {
+            std::array<char, PINN_COMM_ID_BYTES> id{};
+            if (pinn_comm_unique_id(id.data()) != PINN_OK) throw std::runtime_error{"network::comm_id: NCCL is not available"};
+            return id;
+        }
+
+        network &comm_init(const std::array<char, PINN_COMM_ID_BYTES> &id) {
+            this->check(pinn_comm_init(this->ctx, id.data()), "comm_init");
+            return *this;
+        }
+
+        // The two halves of a step for callers that own the collective: local sums, then (after the caller's all-reduce of
+        // gradient_buffer()) the replicated Adam update.
+        network &step_local(void) { this->check(pinn_step_local(this->ctx), "step_local"); return *this; }
+
+        [[nodiscard]] T *gradient_buffer(size_t &n_floats) {
+            return static_cast<T*>(pinn_grad_buffer(this->ctx, &n_floats));
+        }
+
+        step_result step_apply(void) {
+            pinn_step_out o{};
+            this->check(pinn_step_apply(this->ctx, &o), "step_apply");
+            this->device_dirty = true;
+            return network::to_result(o);
         }
 
         // ---- checkpoint + evaluation ----

@@ -187,6 +187,20 @@ int pinn_resample_points(pinn_ctx* ctx, uint64_t seed_interior, uint64_t seed_bo
  * Replaces tensor<float> points = {...} + H2D (tensor.cuh:146-151).  n may not exceed the
  * shard size fixed at create time. */
 int pinn_set_points(pinn_ctx* ctx, int set, const float* x, size_t n);
+/* The same for points that already live on this handle's GPU: d_x is DEVICE memory — e.g. the device half of a
+ * reference tensor<float>, device::tensor::interface<T>::d_var().data (include/device/interface.cuh:248-249), which
+ * tensor::sync_device keeps current (tensor.cuh:72-82).  Device-to-device: no host round trip, no H2D bytes.
+ * A host pointer is refused with PINN_ERR_INVALID_ARGUMENT. */
+int pinn_set_points_device(pinn_ctx* ctx, int set, const float* d_x, size_t n);
+/* ... and from the reference's kernel-argument view itself, device::tensor::variables<float>
+ * (include/device/variables.cuh:6-52): the 48-byte POD every reference kernel takes by value (kernel.cuh:11) —
+ * {T* data @0, size_t* shape @8, size_t* stride @16, size_t dim @24, size_t n @32, bool transposed @40}.
+ * `variables48` points at such a struct in HOST memory (as d_var() returns it); its data pointer is device memory
+ * holding n = n_points * d_in floats, row-major; transposed views are refused. */
+int pinn_set_points_view(pinn_ctx* ctx, int set, const void* variables48);
+/* Host->device bytes this handle has copied for point sets so far (pinn_set_points, pinn_train_step_host's copy
+ * path): lets a caller — and the tests — verify that the device entry points move nothing over PCIe. */
+unsigned long long pinn_h2d_point_bytes(const pinn_ctx* ctx);
 /* Copy this rank's shard of a set back to the host, row-major [n, d_in]. */
 int pinn_get_points(pinn_ctx* ctx, int set, float* x, size_t n);
 /* Local shard size of a set on this rank. */
@@ -208,6 +222,8 @@ int pinn_train_step(pinn_ctx* ctx, pinn_step_out* out);
  * [n, d_in], local shard; pinned memory makes the copy asynchronous), runs the step and
  * reads the loss back.  This is the call bench.py's `e2e` times. */
 int pinn_train_step_host(pinn_ctx* ctx, const float* x_interior, size_t n, pinn_step_out* out);
+/* The same step from interior points that are already on the device (see pinn_set_points_device). */
+int pinn_train_step_device(pinn_ctx* ctx, const float* d_x_interior, size_t n, pinn_step_out* out);
 
 /* k steps back to back without host synchronisation (CUDA-graph replay); losses of the last
  * step are returned. */
@@ -235,6 +251,7 @@ int pinn_synchronize(pinn_ctx* ctx);
 #define PINN_NCCL_ID_BYTES 128
 /* Rank 0 creates the id; the caller distributes the 128 bytes (torch.distributed / MPI /
  * file); every rank then calls pinn_comm_init with its own ctx (cfg.rank / cfg.nranks). */
+#define PINN_COMM_ID_BYTES 128     /* ncclUniqueId */
 int pinn_comm_unique_id(void* id128);
 int pinn_comm_init(pinn_ctx* ctx, const void* id128);
 

@@ -96,7 +96,15 @@ int main(int argc, char **argv) {
 
         network_f net(cfg);
         net.sample();
-        if (!opt.resume.empty()) net.load(opt.resume);
+        size_t resumed_at = 0;                       // Adam step count of the checkpoint: the resample schedule continues from it
+        if (!opt.resume.empty()) {
+            net.load(opt.resume);
+            resumed_at = net.loss().step;
+            if (opt.resample_every && resumed_at >= opt.resample_every) {
+                const size_t epoch = resumed_at / opt.resample_every;      // the point sets the uninterrupted run would be on
+                net.resample(cfg.seed_interior + 16 * epoch, cfg.seed_boundary + 16 * epoch, cfg.seed_initial + 16 * epoch);
+            }
+        }
 
         cout << "pinn_train: pde " << cfg.pde << ", " << cfg.d_in << " -> [" << cfg.width << " x " << cfg.depth << "] -> " << cfg.d_out
              << ", " << net.size() << " parameters, " << net.channels() << " Taylor channels, "
@@ -116,7 +124,8 @@ int main(int argc, char **argv) {
         while(done < opt.steps) {
             // steps between two log lines run back to back on the device (graph replay), one loss read per chunk
             size_t chunk = std::min(opt.log_every, opt.steps - done);
-            if (opt.resample_every) chunk = std::min(chunk, opt.resample_every - done % opt.resample_every);
+            const size_t at = resumed_at + done;     // global step count: a resumed run resamples where the uninterrupted one would
+            if (opt.resample_every) chunk = std::min(chunk, opt.resample_every - at % opt.resample_every);
             last = net.train(chunk);
             done += chunk;
             const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -128,8 +137,8 @@ int main(int argc, char **argv) {
                     csv << last.step << ',' << std::setprecision(9) << last.loss << ',' << last.mse_residual << ',' << last.mse_boundary << ','
                         << last.mse_initial << ',' << seconds << '\n';
             }
-            if (opt.resample_every && done % opt.resample_every == 0) {
-                const size_t epoch = done / opt.resample_every;        // fresh collocation sets: seeds advance by epoch
+            if (opt.resample_every && (resumed_at + done) % opt.resample_every == 0) {
+                const size_t epoch = (resumed_at + done) / opt.resample_every;        // fresh collocation sets: seeds advance by epoch
                 net.resample(cfg.seed_interior + 16 * epoch, cfg.seed_boundary + 16 * epoch, cfg.seed_initial + 16 * epoch);
             }
         }

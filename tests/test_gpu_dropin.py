@@ -80,6 +80,16 @@ def test_network_header_against_reference_tensor(oracle):
     assert kv["xb.shape"].startswith("(256, 2)")
     assert [float(t) for t in kv["xb.shape"].split("xb0=")[1].split(",")] == pytest.approx([float(xb[0, 0]), float(xb[0, 1])], rel=1e-6)
     assert kv["shard"] == "9600,12800"
+    # layer interface, device-resident points, device error channel, rank queries (include/network.cuh)
+    assert kv["layer0"] == "2x20 tanh size=60 layer8=20x1 identity output=1"
+    assert float(kv["layer0.w[0]"]) == float(kv["w0[0]_after"])
+    d = dict(t.split("=") for t in ("dev.step1=" + kv["dev.step1"]).split())
+    assert float(d["dev.step1"]) == pytest.approx(steps[0], rel=1e-6) and float(d["dev.step2"]) == pytest.approx(steps[1], rel=1e-6)
+    assert int(d["dev.h2d_bytes"]) == 0                               # trained from a device pointer: nothing crossed PCIe
+    assert int(kv["dev.h2d_bytes_after_tensor"]) == 4096 * 2 * 4      # reference tensor<T>: device half private -> host upload
+    assert "not a device pointer" in kv["e.hostptr"]
+    assert kv["e.overflow"] == "network::train_step: overflow code=2"
+    assert kv["rank"] == "0/1"
     assert kv["e.assign"] == "network::assign: size mismatch - 7 != 3021"
     assert "pinn_create: width must be a multiple of 4" in kv["e.width"]
     # and the oracle agrees with what the C++ path printed

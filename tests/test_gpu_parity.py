@@ -455,3 +455,64 @@ def test_train_step_host_zero_copy_matches_the_copy_path(P, oracle):
     for mode in ("pinned", "pageable"):
         assert res[mode][0] == res["set_points"][0] and res[mode][1] == [1, 2, 3]
         assert np.array_equal(res[mode][2].view(np.uint32), res["set_points"][2].view(np.uint32))
+
+
+# ------------------------------------------------------------------ error channel, device-resident inputs
+def test_overflow_reaches_the_caller_as_device_overflow_and_clears(P, oracle):
+    """Reference error channel (include/device/runtime.cuh:17-47: device code -> device_exception{code, name}): parameters of
+    1e30 make the loss non-finite; the step returns PINN_ERR_DEVICE_OVERFLOW (2) with the reference's message form, the flag
+    is cleared, and the handle works again after sane parameters are restored."""
+    ocfg = oracle.baseline_config(1)
+    for prec in (0, 4):
+        with P.Network(pcfg(P, ocfg, precision=prec)) as net:
+            w = net.get_params()
+            net.set_params(np.full_like(w, 1e30))
+            with pytest.raises(P.PinnError) as ei:
+                net.train_step()
+            assert ei.value.code == 2 and "network::train_step: overflow" in str(ei.value)
+            with pytest.raises(P.PinnError) as ei:
+                net.loss_grad()
+            assert ei.value.code == 2
+            net.set_params(w)
+            out = net.loss_grad()
+            assert np.isfinite(out["loss"])
+            net.train_step()
+
+
+def test_sharded_handle_without_a_communicator_refuses_the_fused_step(P, oracle):
+    """nranks > 1 and no communicator: the fused entry points would scale LOCAL sums by GLOBAL counts — refused."""
+    ocfg = oracle.baseline_config(1)
+    with P.Network(pcfg(P, ocfg, rank=1, nranks=2)) as net:
+        for call in (net.train_step, lambda: net.train_steps(2)):
+            with pytest.raises(P.PinnError) as ei:
+                call()
+            assert ei.value.code == 3 and "no communicator" in str(ei.value)
+        net.step_local()                                   # the caller-owned collective path stays available
+
+
+def test_device_resident_points_train_without_host_to_device_bytes(P, oracle):
+    """pinn_set_points_device / pinn_train_step_device / pinn_set_points_view: points that already live on the GPU (the device
+    half of a reference tensor<float>, interface.cuh:248-249; its kernel-argument view variables<T>, variables.cuh:6-52) are
+    bound device-to-device.  Same losses, bit for bit, as the host upload path; zero H2D point bytes."""
+    import torch
+    ocfg = oracle.baseline_config(2)
+    xf = oracle.sample(ocfg, 0)[::-1].copy()               # a point set that differs from the resident one
+    with P.Network(pcfg(P, ocfg, precision=4)) as a, P.Network(pcfg(P, ocfg, precision=4)) as b:
+        xd = torch.from_numpy(xf).cuda()
+        la = [a.train_step_host(xf, len(xf))["loss"] for _ in range(3)]
+        assert a.h2d_point_bytes() > 0
+        lb = [b.train_step_device(xd.data_ptr(), len(xf))["loss"] for _ in range(3)]
+        assert b.h2d_point_bytes() == 0
+        assert la == lb
+        assert np.array_equal(a.get_params().view(np.uint32), b.get_params().view(np.uint32))
+        assert np.array_equal(b.get_points(0).view(np.uint32), xf.view(np.uint32))
+        # the reference kernel-argument view (48-byte POD) on the boundary set
+        xb = torch.from_numpy(oracle.sample(ocfg, 1)).cuda()
+        b.set_points_view(1, xb.data_ptr(), xb.numel())
+        assert np.array_equal(b.get_points(1), xb.cpu().numpy()) and b.h2d_point_bytes() == 0
+        with pytest.raises(P.PinnError) as ei:
+            b.set_points_view(1, xb.data_ptr(), xb.numel(), transposed=True)
+        assert ei.value.code == 3
+        with pytest.raises(P.PinnError) as ei:                  # a host pointer is not a device pointer
+            b.set_points_device(0, xf.ctypes.data, len(xf))
+        assert ei.value.code == 3
