@@ -20,6 +20,7 @@
 #include "pinn_fused_fp32.cuh"
 #include "pinn_fused_tc.cuh"
 #include "pinn_fused_tc2.cuh"
+#include "pinn_fused_tc3.cuh"
 #include "pinn_fused_warp.cuh"
 #include "pinn_fused_mma.cuh"
 
@@ -460,7 +461,7 @@ struct pinn_ctx {
     // producer / dW-server tensor-core kernel (pinn_fused_tc2.cuh): training launches of the interior set, widths 128 / 256
     typedef void (*tc2_fn)(const NetDims, const Tc2Args);
     tc2_fn kern_tc2 = nullptr;
-    int tc2_q = 0, tc2_nprod = 0, tc2_zdepth = 4, tc2_smem = 0;
+    int tc2_q = 0, tc2_nprod = 0, tc2_zdepth = 4, tc2_smem = 0, tc2_T = tc2::T, tc2_threads = 0;   // tc2_T: points per producer tile (tc3: 20)
     __nv_bfloat16 *d_wf = nullptr, *d_wb = nullptr;
     uint8_t *d_st_a = nullptr, *d_st_s = nullptr, *d_zring = nullptr;
     unsigned int* d_tc2_flags = nullptr;
@@ -769,16 +770,20 @@ static int configure_kernels(pinn_ctx* c) {
                 int coop = 0;
                 CUDA_TRY(c, "pinn_create", cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->cfg.device));
                 if (coop && nprod >= 8 && smem2 <= max_smem) {
-                    c->kern_tc2 = H == 128 ? fused_step_tc2<3, 2, 128> : fused_step_tc2<3, 2, 256>;
+                    // default producer: two sub-tiles in flight (pinn_fused_tc3.cuh); PINN_TC3=0 keeps the one-tile producer of tc2
+                    const char* e3 = getenv("PINN_TC3");
+                    const bool tc3on = !(e3 && atoi(e3) == 0);
+                    if (tc3on) { c->kern_tc2 = H == 128 ? fused_step_tc3<3, 2, 128> : fused_step_tc3<3, 2, 256>; c->tc2_T = tc3::T; c->tc2_threads = 2 * H; }
+                    else { c->kern_tc2 = H == 128 ? fused_step_tc2<3, 2, 128> : fused_step_tc2<3, 2, 256>; c->tc2_T = tc2::T; c->tc2_threads = 2 * H; }
                     CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
                     int occ2 = 0;
-                    CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, c->kern_tc2, 2 * H, smem2));
+                    CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, c->kern_tc2, c->tc2_threads, smem2));
                     if (occ2 < 1) c->kern_tc2 = nullptr;
                     else {
                         c->tc2_q = q; c->tc2_nprod = nprod; c->tc2_smem = smem2;
                         if (const char* ez = getenv("PINN_TC2_ZD")) c->tc2_zdepth = atoi(ez);
                         if (c->tc2_zdepth < 2) c->tc2_zdepth = 2;
-                        c->kernel_id = 110 + nterms;
+                        c->kernel_id = (tc3on ? 120 : 110) + nterms;
                     }
                 }
             }
@@ -901,13 +906,16 @@ static int launch_tc2(pinn_ctx* c, const PointSet& interior, int* rows_out) {
     *rows_out = 0;
     if (interior.n == 0) return PINN_OK;
     Tc2Args a{};
-    a.params = c->d_params; a.set = interior; a.set.ntiles = tiles_of(interior.n, tc2::T);
+    a.params = c->d_params; a.set = interior; a.set.ntiles = tiles_of(interior.n, c->tc2_T);
     a.partial = c->d_partial; a.row0 = 0;
     a.wf = c->d_wf; a.wb = c->d_wb; a.stash_a = c->d_st_a; a.stash_s = c->d_st_s; a.zring = c->d_zring;
     a.ready = c->d_tc2_flags; a.done = c->d_tc2_flags + (size_t)c->tc2_nprod * kFlagStride;
+    a.stagger = 4;
+    if (const char* es = getenv("PINN_TC3_STAGGER")) a.stagger = atoi(es);
+    a.ready2 = c->tc2_T == tc3::T ? c->d_tc2_flags + 2 * (size_t)c->tc2_nprod * kFlagStride : nullptr;
     a.nprod = c->tc2_nprod; a.q = c->tc2_q; a.zdepth = c->tc2_zdepth; a.dbg = c->d_tc2_dbg;
     a.trap_site = reinterpret_cast<int*>(c->d_hrec + 16);
-    CUDA_TRY(c, "pinn_train_step", cudaMemsetAsync(c->d_tc2_flags, 0, 2 * (size_t)c->tc2_nprod * kFlagStride * sizeof(unsigned int), c->stream));
+    CUDA_TRY(c, "pinn_train_step", cudaMemsetAsync(c->d_tc2_flags, 0, 3 * (size_t)c->tc2_nprod * kFlagStride * sizeof(unsigned int), c->stream));
     const bool timed = c->prof && !c->capturing;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {
@@ -917,7 +925,7 @@ static int launch_tc2(pinn_ctx* c, const PointSet& interior, int* rows_out) {
     NetDims nd = c->nd;
     void* kargs[] = {&nd, &a};
     CUDA_TRY(c, "pinn_train_step", cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(c->kern_tc2), dim3(c->num_sms),
-                                                               dim3(2 * c->nd.H), kargs, (size_t)c->tc2_smem, c->stream));
+                                                               dim3(c->tc2_threads), kargs, (size_t)c->tc2_smem, c->stream));
     if (timed) { CUDA_TRY(c, "pinn_train_step", cudaEventRecord(e1, c->stream)); c->pending.emplace_back(e0, e1); }
     c->last_grid = c->num_sms;
     *rows_out = c->num_sms;
@@ -1012,7 +1020,7 @@ static void refresh_wq(pinn_ctx* c, bool after_adam) {
     }
     if (c->d_wf) {
         const long long n2 = (long long)(c->nd.L - 1) * c->nd.H * c->nd.H;
-        pack_w2_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, c->stream>>>(c->nd, c->d_params, c->d_wf, c->d_wb);
+        pack_w2_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, c->stream>>>(c->nd, c->d_params, c->d_wf, c->d_wb, c->tc2_T == tc3::T ? 1 : 0);
         c->step_launches++;
     }
     if (!c->d_wq) return;
@@ -1254,12 +1262,12 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
         TRY_C(cudaMalloc(&c->d_st_a, np * nd.L * opb));
         TRY_C(cudaMalloc(&c->d_st_s, np * nd.L * tc2::NGRP * nd.H * 8));
         TRY_C(cudaMalloc(&c->d_zring, np * c->tc2_zdepth * opb));
-        TRY_C(cudaMalloc(&c->d_tc2_flags, 2 * np * kFlagStride * sizeof(unsigned int)));
+        TRY_C(cudaMalloc(&c->d_tc2_flags, 3 * np * kFlagStride * sizeof(unsigned int)));
         if (const char* ts = getenv("PINN_TC2_TIMEOUT_SHIFT")) {   // under a profiler every hand-off is slower: relax the wait bounds
             const long long bound = 1LL << (30 + atoi(ts));
             TRY_C(cudaMemcpyToSymbol(tc2::g_wait_bound, &bound, sizeof(bound)));
         }
-        if (getenv("PINN_TC2_DBG")) { TRY_C(cudaMalloc(&c->d_tc2_dbg, 8 * sizeof(long long))); TRY_C(cudaMemsetAsync(c->d_tc2_dbg, 0, 8 * sizeof(long long), c->stream)); }
+        if (getenv("PINN_TC2_DBG")) { TRY_C(cudaMalloc(&c->d_tc2_dbg, 512 * sizeof(long long))); TRY_C(cudaMemsetAsync(c->d_tc2_dbg, 0, 512 * sizeof(long long), c->stream)); }
     }
     TRY_C(cudaMalloc(&c->d_loss, 8 * sizeof(float)));          // [0..3] loss record, [4] overflow flag word: one D2H copy per read-back
     TRY_C(cudaMalloc(&c->d_step, sizeof(unsigned long long)));
@@ -1294,8 +1302,28 @@ void pinn_destroy(pinn_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     drain_profile(c);
     if (c->d_tc2_dbg) {
-        long long h[8] = {0};
-        if (cudaMemcpy(h, c->d_tc2_dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
+        long long h[512] = {0};
+        if (cudaMemcpy(h, c->d_tc2_dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && c->tc2_T == tc3::T) {
+            fprintf(stderr, "[tc3 dbg] cycles of producer 0, last launch: issuer A waits ready %lld  weights %lld  issue %lld | thread 0: umma wait %lld  fwd epi %lld  rev epi %lld  out %lld  total %lld\n",
+                    h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+            fprintf(stderr, "[tc3 dbg] thread 0 reverse epilogues (l < L): TMEM loads %lld  fences + arrive %lld  body %lld\n", h[8], h[10], h[11]);
+            // timeline of one tile (PINN_TC2_DBG=2 prints it): cycles since the first stamp of the tile
+            if (atoi(getenv("PINN_TC2_DBG") ? getenv("PINN_TC2_DBG") : "0") >= 2) {
+                const int spt = 2 * (c->nd.L - 1);
+                long long t0 = h[16];
+                for (int s = 0; s < spt; s++)
+                    for (int x = 0; x < 2; x++) {
+                        const long long* e = h + 16 + (s * 2 + x) * 8;
+                        fprintf(stderr, "  step %2d issuer %c: start %6lld  ready %6lld  weights0 %6lld  [m0] issued %6lld  weights1 %6lld  [m1] issued %6lld\n", s, 'A' + x,
+                                e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0, e[5] - t0);
+                    }
+                for (int pc = 0; pc < 2 * (c->nd.H / 128); pc++) {
+                    fprintf(stderr, "  piece %d epilogues (start..end):", pc);
+                    for (int k = 0; k < 2 * c->nd.L; k++) fprintf(stderr, " %lld..%lld", h[272 + (pc * 16 + k) * 2] - t0, h[273 + (pc * 16 + k) * 2] - t0);
+                    fprintf(stderr, "\n");
+                }
+            }
+        } else
             fprintf(stderr, "[tc2 dbg] cycles of producer 0, last launch: fwd wait %lld  fwd epi %lld  out %lld  rev wait %lld  rev epi %lld  rev issue %lld  layer1 %lld  total %lld\n",
                     h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
         cudaFree(c->d_tc2_dbg);
@@ -1787,7 +1815,7 @@ int pinn_profile_get(pinn_ctx* c, pinn_profile* out, int reset) {
     out->launches = c->launches; out->step_kernel_ms = c->kernel_ms; out->step_kernel_count = c->kernel_count;
     out->grid = c->last_grid;
     // launch shape of the kernel the interior training launch runs (the mma.sync kernel used to report the FP32 kernel's)
-    out->block = c->kern_mma ? kMmaWarps * 32 : (c->kern_tc2 ? 2 * c->nd.H : (c->kern_tc ? c->tc_threads : (c->kern_warp ? c->warp_wpc * 32 : c->threads)));
+    out->block = c->kern_mma ? kMmaWarps * 32 : (c->kern_tc2 ? c->tc2_threads : (c->kern_tc ? c->tc_threads : (c->kern_warp ? c->warp_wpc * 32 : c->threads)));
     out->smem_bytes = c->kern_mma ? c->mma_smem : (c->kern_tc2 ? c->tc2_smem : (c->kern_tc ? c->tc_smem : (c->kern_warp ? c->warp_smem : c->smem_full)));
     out->kernel_id = c->kernel_id;
     if (reset) { c->launches = 0; c->kernel_ms = 0.0; c->kernel_count = 0; }

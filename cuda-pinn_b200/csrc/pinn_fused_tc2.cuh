@@ -47,8 +47,10 @@ struct Tc2Args {
     uint8_t* stash_s;              // [nprod][L][6][H][4] bf16   s = 1 - a^2
     uint8_t* zring;                // [nprod][zdepth][H*256 B]  Zbar images on their way to the dW servers
     unsigned int* ready;           // [nprod][kFlagStride]  ready[p][l] = t+1: Zbar_l (and A_{l-1}) of tile t are in memory
+    unsigned int* ready2;          // tc3 only (else null): the same flag for the second sub-tile's half of the images; the server waits for both
     unsigned int* done;            // [nprod][kFlagStride]  done[p][l]  = t+1: server has both operands of tile t on chip
     int nprod, q, zdepth;
+    int stagger;                   // tc3: sub-tile B issues a layer step once A has issued this many of its weight pieces (0 = free-running)
     long long* dbg;                // optional [8]: cycle counters of producer 0 (PINN_TC2_DBG=1), or null
     int* trap_site;                // mapped host memory [4]: {site, block, a, b} of a wait that timed out (see tc2::trap_at)
 };
@@ -195,6 +197,96 @@ inline int tc2_smem_bytes(int H, int L) {
     return producer > server ? producer : server;
 }
 
+// =====================================================================================
+// dW server CTA (shared by the tc2 and tc3 producer kernels): dW_l = sum over its producers' tiles of A_{l-1}^T Zbar_l,
+// accumulated in TMEM over the whole step, drained once into the CTA's own partial row.
+// =====================================================================================
+template <int HT>
+__device__ __forceinline__ void dw_server(const NetDims& nd, const Tc2Args& ta, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
+                                          uint64_t* fin_bar_p, uint32_t tmem, float* part) {
+    using namespace tc2;
+    constexpr int H = HT, MT = H / 128;
+    constexpr uint32_t OPB = (uint32_t)H * 256u, CHS = (uint32_t)H * 16u;
+    const int L = nd.L;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q4 = warp & 3, mt = (warp >> 2) % MT, half = (warp >> 2) / MT;
+    const int j = mt * 128 + q4 * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    const int ntiles = ta.set.ntiles, P = ta.nprod;
+    uint64_t& fin_bar = *fin_bar_p;
+    const int ci = (int)blockIdx.x - P, l = 2 + ci / ta.q, i0 = ci % ta.q;
+    constexpr uint32_t HALF = OPB / 2;              // 8 n-chunks of both operands per pipeline stage
+    bool any_work = false;
+    for (int p = i0; p < P; p += ta.q) any_work |= tiles_of_producer(ntiles, p, P) > 0;
+    if (warp == 0 && lane == 0) {                   // ---- loader ----
+        unsigned it = 0;
+        for (int t = 0;; t++) {
+            bool any = false;
+            for (int p = i0; p < P; p += ta.q) {
+                if (t >= tiles_of_producer(ntiles, p, P)) continue;
+                any = true;
+                wait_ge_at(ta.ready + (size_t)p * kFlagStride + l, (unsigned)t + 1u, ta.trap_site, 111);
+                if (ta.ready2) wait_ge_at(ta.ready2 + (size_t)p * kFlagStride + l, (unsigned)t + 1u, ta.trap_site, 122);
+                fence_proxy_async_all();
+                const unsigned item = (unsigned)t * (unsigned)(L - 1) + (unsigned)(L - l);
+                // A_{l-1}; A_1 has two copies (tile parity; the second one in the unused slot of A_L), see the producer
+                const uint8_t* srcA = ta.stash_a + ((size_t)p * L + ((l == 2 && (t & 1)) ? L - 1 : l - 2)) * OPB;
+                const uint8_t* srcZ = ta.zring + ((size_t)p * ta.zdepth + item % (unsigned)ta.zdepth) * OPB;
+                for (int h = 0; h < 2; h++, it++) {
+                    const unsigned st = it % 3u;
+                    if (it >= 3u) mbar_wait_at(&empty_bar[st], ((it / 3u) - 1u) & 1u, ta.trap_site, 101);
+                    umma::mbar_expect_tx(&full_bar[st], 2 * HALF);
+                    umma::bulk_g2s(smem + (size_t)st * OPB, srcA + (size_t)h * HALF, HALF, &full_bar[st]);
+                    umma::bulk_g2s(smem + (size_t)st * OPB + HALF, srcZ + (size_t)h * HALF, HALF, &full_bar[st]);
+                }
+            }
+            if (!any) break;
+        }
+    } else if (warp == 1 && lane == 0) {            // ---- MMA issuer ----
+        unsigned it = 0;
+        for (int t = 0;; t++) {
+            bool any = false;
+            for (int p = i0; p < P; p += ta.q) {
+                if (t >= tiles_of_producer(ntiles, p, P)) continue;
+                any = true;
+                for (int h = 0; h < 2; h++, it++) {
+                    const unsigned st = it % 3u;
+                    mbar_wait_at(&full_bar[st], (it / 3u) & 1u, ta.trap_site, 102);
+                    umma::tc_fence_after();
+                    const uint32_t sa = umma::smem_u32(smem + (size_t)st * OPB), sz = sa + HALF;
+                    // both operands K-major over n: 8-column chunks CHS apart, 8 rows (units) 128 B apart
+                    #pragma unroll
+                    for (int m = 0; m < MT; m++)
+                        umma::gemm_issue(tmem + (uint32_t)(m * H), sa + (uint32_t)m * 2048u, CHS, 128, 2 * CHS,
+                                         sz, CHS, 128, 2 * CHS, umma::idesc_bf16(128, H, 0, 0), 4, it > 0 ? 1u : 0u);
+                    umma::mma_commit(&empty_bar[st]);
+                }
+                st_release(ta.done + (size_t)p * kFlagStride + l, (unsigned)t + 1u);   // both operand images are on chip
+            }
+            if (!any) break;
+        }
+        umma::mma_commit(&fin_bar);
+    }
+    mbar_wait_at(&fin_bar, 0, ta.trap_site, 103);
+    umma::tc_fence_after();
+    if (any_work && tid < 2 * HT) {                 // drain: lane = fan-in unit k, columns = units j (tc3 launches one more warp)
+        float* dst = part + nd.offW[l] + (size_t)j * H;
+        for (int c = half * (H / 2); c < (half + 1) * (H / 2); c += 16) {
+            uint32_t r[16];
+            tmem_ld16_nowait(tmem + lane_addr + (uint32_t)(mt * H + c), r);
+            umma::tmem_ld_wait();
+            #pragma unroll
+            for (int v = 0; v < 4; v++)
+                *reinterpret_cast<float4*>(dst + c + 4 * v) =
+                    make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                                __uint_as_float(r[4 * v + 3]));
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 512u);
+}
+
 template <int DIN, int N2, int HT>
 __global__ void __launch_bounds__(2 * HT, 1)
 fused_step_tc2(const NetDims nd, const Tc2Args ta) {
@@ -234,79 +326,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     const int ntiles = ta.set.ntiles, P = ta.nprod;
 
     if ((int)blockIdx.x >= P) {
-        // =====================================================================================
-        // dW server: dW_l = sum over its producers' tiles of A_{l-1}^T Zbar_l, accumulated in TMEM
-        // =====================================================================================
-        const int ci = (int)blockIdx.x - P, l = 2 + ci / ta.q, i0 = ci % ta.q;
-        constexpr uint32_t HALF = OPB / 2;              // 8 n-chunks of both operands per pipeline stage
-        bool any_work = false;
-        for (int p = i0; p < P; p += ta.q) any_work |= tiles_of_producer(ntiles, p, P) > 0;
-        if (warp == 0 && lane == 0) {                   // ---- loader ----
-            unsigned it = 0;
-            for (int t = 0;; t++) {
-                bool any = false;
-                for (int p = i0; p < P; p += ta.q) {
-                    if (t >= tiles_of_producer(ntiles, p, P)) continue;
-                    any = true;
-                    wait_ge_at(ta.ready + (size_t)p * kFlagStride + l, (unsigned)t + 1u, ta.trap_site, 111);
-                    fence_proxy_async_all();
-                    const unsigned item = (unsigned)t * (unsigned)(L - 1) + (unsigned)(L - l);
-                    // A_{l-1}; A_1 has two copies (tile parity; the second one in the unused slot of A_L), see the producer
-                    const uint8_t* srcA = ta.stash_a + ((size_t)p * L + ((l == 2 && (t & 1)) ? L - 1 : l - 2)) * OPB;
-                    const uint8_t* srcZ = ta.zring + ((size_t)p * ta.zdepth + item % (unsigned)ta.zdepth) * OPB;
-                    for (int h = 0; h < 2; h++, it++) {
-                        const unsigned st = it % 3u;
-                        if (it >= 3u) mbar_wait_at(&empty_bar[st], ((it / 3u) - 1u) & 1u, ta.trap_site, 101);
-                        umma::mbar_expect_tx(&full_bar[st], 2 * HALF);
-                        umma::bulk_g2s(smem + (size_t)st * OPB, srcA + (size_t)h * HALF, HALF, &full_bar[st]);
-                        umma::bulk_g2s(smem + (size_t)st * OPB + HALF, srcZ + (size_t)h * HALF, HALF, &full_bar[st]);
-                    }
-                }
-                if (!any) break;
-            }
-        } else if (warp == 1 && lane == 0) {            // ---- MMA issuer ----
-            unsigned it = 0;
-            for (int t = 0;; t++) {
-                bool any = false;
-                for (int p = i0; p < P; p += ta.q) {
-                    if (t >= tiles_of_producer(ntiles, p, P)) continue;
-                    any = true;
-                    for (int h = 0; h < 2; h++, it++) {
-                        const unsigned st = it % 3u;
-                        mbar_wait_at(&full_bar[st], (it / 3u) & 1u, ta.trap_site, 102);
-                        umma::tc_fence_after();
-                        const uint32_t sa = umma::smem_u32(smem + (size_t)st * OPB), sz = sa + HALF;
-                        // both operands K-major over n: 8-column chunks CHS apart, 8 rows (units) 128 B apart
-                        #pragma unroll
-                        for (int m = 0; m < MT; m++)
-                            umma::gemm_issue(tmem + (uint32_t)(m * H), sa + (uint32_t)m * 2048u, CHS, 128, 2 * CHS,
-                                             sz, CHS, 128, 2 * CHS, umma::idesc_bf16(128, H, 0, 0), 4, it > 0 ? 1u : 0u);
-                        umma::mma_commit(&empty_bar[st]);
-                    }
-                    st_release(ta.done + (size_t)p * kFlagStride + l, (unsigned)t + 1u);   // both operand images are on chip
-                }
-                if (!any) break;
-            }
-            umma::mma_commit(&fin_bar);
-        }
-        mbar_wait_at(&fin_bar, 0, ta.trap_site, 103);
-        umma::tc_fence_after();
-        if (any_work) {                                 // drain: lane = fan-in unit k, columns = units j
-            float* dst = part + nd.offW[l] + (size_t)j * H;
-            for (int c = half * (H / 2); c < (half + 1) * (H / 2); c += 16) {
-                uint32_t r[16];
-                tmem_ld16_nowait(tmem + lane_addr + (uint32_t)(mt * H + c), r);
-                umma::tmem_ld_wait();
-                #pragma unroll
-                for (int v = 0; v < 4; v++)
-                    *reinterpret_cast<float4*>(dst + c + 4 * v) =
-                        make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
-                                    __uint_as_float(r[4 * v + 3]));
-            }
-        }
-        umma::tc_fence_before();
-        __syncthreads();
-        if (warp == 0) umma::tmem_dealloc(tmem, 512u);
+        dw_server<HT>(nd, ta, smem, full_bar, empty_bar, &fin_bar, tmem, part);
         return;
     }
 
@@ -816,8 +836,10 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
 }
 
 // BF16 mirrors of the hidden->hidden weights in the two slab layouts of Tc2Args (wf, wb).
+// khalf = 1 (tc3): the forward mirror keeps each 128-wide half of K contiguous, [j/128][k/128][(j%128)/8][k%128][j%8], so that
+// a 32 KB piece (M-tile x K-half) is one bulk copy; the reverse mirror already is (its K runs over the j-chunks).
 __global__ void pack_w2_kernel(const NetDims nd, const float* __restrict__ params, __nv_bfloat16* __restrict__ wf,
-                               __nv_bfloat16* __restrict__ wb) {
+                               __nv_bfloat16* __restrict__ wb, int khalf) {
     const int H = nd.H, MT = H / 128;
     const long long n = (long long)(nd.L - 1) * H * H;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -827,7 +849,8 @@ __global__ void pack_w2_kernel(const NetDims nd, const float* __restrict__ param
     const __nv_bfloat16 w = __float2bfloat16(params[nd.offW[l] + r]);
     const size_t lbase = (size_t)(l - 2) * H * H;
     // forward: [j/128][ (j%128)/8 ][k][j%8]
-    wf[lbase + (size_t)(j >> 7) * (128 * H) + (size_t)((j & 127) >> 3) * (H * 8) + (size_t)k * 8 + (j & 7)] = w;
+    if (khalf) wf[lbase + (size_t)(j >> 7) * (128 * H) + (size_t)(k >> 7) * (128 * 128) + (size_t)((j & 127) >> 3) * (128 * 8) + (size_t)(k & 127) * 8 + (j & 7)] = w;
+    else wf[lbase + (size_t)(j >> 7) * (128 * H) + (size_t)((j & 127) >> 3) * (H * 8) + (size_t)k * 8 + (j & 7)] = w;
     // reverse: [k/128][ j/8 ][k%128][j%8]
     wb[lbase + (size_t)(k >> 7) * (128 * H) + (size_t)(j >> 3) * (128 * 8) + (size_t)(k & 127) * 8 + (j & 7)] = w;
     (void)MT;

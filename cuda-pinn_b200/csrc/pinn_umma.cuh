@@ -127,6 +127,35 @@ __device__ __forceinline__ void gemm_issue(uint32_t d_tmem, uint32_t a_addr, uin
                  (s > 0) ? 1u : accumulate_first);
 }
 
+// ---- lean issue path (tc3) ------------------------------------------------------------------
+// One UMMA per ~16 SASS instructions (descriptor rebuilt from the address, an ELECT loop around every tcgen05.mma because the
+// compiler cannot see that a `tid == k` branch holds one lane) makes a single issuing thread the bottleneck: ~94 cycles per UMMA
+// against 69 of execution.  Here the descriptor words are built once per contraction and stepped by an add, and the issuing lane
+// comes from elect.sync inside a warp-uniform branch.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ void mma_bf16_words(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <int KSTEPS>
+__device__ __forceinline__ void gemm_issue_lean(uint32_t d_tmem, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep,
+                                                uint32_t b_addr, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep,
+                                                uint32_t idesc, uint32_t accumulate_first) {
+    const uint32_t a_lo = desc_lo(a_addr, a_lbo), a_hi = desc_hi(a_sbo), b_lo = desc_lo(b_addr, b_lbo), b_hi = desc_hi(b_sbo);
+    #pragma unroll
+    for (int s = 0; s < KSTEPS; s++)
+        mma_bf16_words(d_tmem, a_lo + (uint32_t)s * (a_kstep >> 4), a_hi, b_lo + (uint32_t)s * (b_kstep >> 4), b_hi, idesc,
+                       (s > 0) ? 1u : accumulate_first);
+}
+
 // byte offset of element (r, f) of an [R x F] bf16 matrix in the chunk-major layout above
 __host__ __device__ __forceinline__ uint32_t cm_offset(int r, int f, int R) { return (uint32_t)((f >> 3) * (R * 16) + r * 16 + (f & 7) * 2); }
 
