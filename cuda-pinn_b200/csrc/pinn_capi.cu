@@ -773,7 +773,7 @@ static int configure_kernels(pinn_ctx* c) {
                     // default producer: two sub-tiles in flight (pinn_fused_tc3.cuh); PINN_TC3=0 keeps the one-tile producer of tc2
                     const char* e3 = getenv("PINN_TC3");
                     const bool tc3on = !(e3 && atoi(e3) == 0);
-                    if (tc3on) { c->kern_tc2 = H == 128 ? fused_step_tc3<3, 2, 128> : fused_step_tc3<3, 2, 256>; c->tc2_T = tc3::T; c->tc2_threads = 2 * H; }
+                    if (tc3on) { c->kern_tc2 = H == 128 ? fused_step_tc3<3, 2, 128> : fused_step_tc3<3, 2, 256>; c->tc2_T = tc3::T; c->tc2_threads = 2 * H + tc3::kHelperThreads; }
                     else { c->kern_tc2 = H == 128 ? fused_step_tc2<3, 2, 128> : fused_step_tc2<3, 2, 256>; c->tc2_T = tc2::T; c->tc2_threads = 2 * H; }
                     CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
                     int occ2 = 0;
@@ -1304,24 +1304,23 @@ void pinn_destroy(pinn_ctx* c) {
     if (c->d_tc2_dbg) {
         long long h[512] = {0};
         if (cudaMemcpy(h, c->d_tc2_dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && c->tc2_T == tc3::T) {
-            fprintf(stderr, "[tc3 dbg] cycles of producer 0, last launch: issuer A waits ready %lld  weights %lld  issue %lld | thread 0: umma wait %lld  fwd epi %lld  rev epi %lld  out %lld  total %lld\n",
-                    h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
-            fprintf(stderr, "[tc3 dbg] thread 0 reverse epilogues (l < L): TMEM loads %lld  fences + arrive %lld  body %lld\n", h[8], h[10], h[11]);
+            fprintf(stderr, "[tc3 dbg] cycles of producer 0, last launch | epilogue thread 0: waits %lld  layer-1 %lld  fwd epi %lld  out + rev L %lld  rev epi %lld  total %lld\n",
+                    h[0], h[1], h[2], h[3], h[4], h[7]);
+            fprintf(stderr, "[tc3 dbg] forward epilogues of thread 0: TMEM load %lld  math + stores %lld  fences + arrive %lld\n", h[8], h[9], h[10]);
             // timeline of one tile (PINN_TC2_DBG=2 prints it): cycles since the first stamp of the tile
             if (atoi(getenv("PINN_TC2_DBG") ? getenv("PINN_TC2_DBG") : "0") >= 2) {
-                const int spt = 2 * (c->nd.L - 1);
-                long long t0 = h[16];
-                for (int s = 0; s < spt; s++)
+                const int L = c->nd.L;
+                const long long t0 = h[160];
+                for (int e = 0; e < 2 * L - 1; e++)
                     for (int x = 0; x < 2; x++) {
-                        const long long* e = h + 16 + (s * 2 + x) * 8;
-                        fprintf(stderr, "  step %2d issuer %c: start %6lld  ready %6lld  weights0 %6lld  [m0] issued %6lld  weights1 %6lld  [m1] issued %6lld\n", s, 'A' + x,
-                                e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0, e[5] - t0);
+                        const long long* r = h + 16 + (e * 2 + x) * 4;
+                        fprintf(stderr, "  event %2d issuer %c: start %6lld  ready %6lld  (weights %5lld)  issued %6lld\n", e, 'A' + x, r[0] - t0, r[1] - t0, r[2] - r[1], r[3] - t0);
                     }
-                for (int pc = 0; pc < 2 * (c->nd.H / 128); pc++) {
-                    fprintf(stderr, "  piece %d epilogues (start..end):", pc);
-                    for (int k = 0; k < 2 * c->nd.L; k++) fprintf(stderr, " %lld..%lld", h[272 + (pc * 16 + k) * 2] - t0, h[273 + (pc * 16 + k) * 2] - t0);
-                    fprintf(stderr, "\n");
-                }
+                for (int ph = 0; ph < 2 * L; ph++)
+                    for (int x = 0; x < 2; x++) {
+                        const long long* r = h + 160 + (ph * 2 + x) * 3;
+                        fprintf(stderr, "  phase %2d %c epilogue: enter %6lld  work %6lld .. %6lld\n", ph, 'A' + x, r[0] - t0, r[1] - t0, r[2] - t0);
+                    }
             }
         } else
             fprintf(stderr, "[tc2 dbg] cycles of producer 0, last launch: fwd wait %lld  fwd epi %lld  out %lld  rev wait %lld  rev epi %lld  rev issue %lld  layer1 %lld  total %lld\n",
