@@ -90,6 +90,17 @@ def lib():
     L.pinn_num_params.argtypes = [cfgp]; L.pinn_num_params.restype = C.c_size_t
     L.pinn_shard_range.argtypes = [C.c_uint64, C.c_int32, C.c_int32, P(C.c_uint64), P(C.c_uint64)]
     L.pinn_shard_range.restype = None
+    # include/pinn_tensor_abi.h: device-resident tensor operations
+    sz = C.c_size_t
+    L.pinn_tensor_elementwise.argtypes = [C.c_int, C.c_int, vp, sz, vp, sz, vp, sz, C.c_int, vp]
+    L.pinn_tensor_matmul.argtypes = [C.c_int, vp, C.c_int, vp, C.c_int, vp, sz, sz, sz, vp]
+    L.pinn_tensor_dot_scratch.argtypes = [sz]; L.pinn_tensor_dot_scratch.restype = sz
+    L.pinn_tensor_dot.argtypes = [C.c_int, vp, vp, sz, vp, vp, vp]
+    L.pinn_tensor_add_multiple.argtypes = [C.c_int, P(vp), sz, sz, vp, vp]
+    L.pinn_device_alloc.argtypes = [P(vp), sz, vp]
+    L.pinn_device_free.argtypes = [vp, vp]
+    L.pinn_device_upload.argtypes = [vp, vp, sz, vp]
+    L.pinn_device_download.argtypes = [vp, vp, sz, vp]
     L.pinn_create.argtypes = [P(vp), cfgp]
     L.pinn_destroy.argtypes = [vp]; L.pinn_destroy.restype = None
     L.pinn_last_error.argtypes = [vp]; L.pinn_last_error.restype = C.c_char_p
@@ -374,3 +385,85 @@ class Network:
         self._check(self._L.pinn_profile_get(self._h, C.byref(p), int(reset)))
         return dict(launches=int(p.launches), step_kernel_ms=p.step_kernel_ms, step_kernel_count=int(p.step_kernel_count),
                     grid=p.grid, block=p.block, smem_bytes=p.smem_bytes, kernel_id=p.kernel_id)
+
+
+# ---------------------------------------------------------------------------------------------
+# include/pinn_tensor_abi.h — device-resident tensor operations (pass-through; no arithmetic here)
+# ---------------------------------------------------------------------------------------------
+OP_ADD, OP_SUB, OP_MUL, OP_DIV = 0, 1, 2, 3
+
+
+class DeviceArray:
+    """A flat device buffer of float32 / float64 owned through pinn_device_alloc / pinn_device_free."""
+
+    def __init__(self, data=None, n=None, dtype=np.float32):
+        self._L = lib()
+        if data is not None:
+            data = np.ascontiguousarray(data)
+            dtype, n = data.dtype, data.size
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise ValueError("float32 or float64")
+        self.n = int(n)
+        self.ptr = C.c_void_p()
+        rc = self._L.pinn_device_alloc(C.byref(self.ptr), self.n * self.dtype.itemsize, None)
+        if rc:
+            raise PinnError(rc, "pinn_device_alloc failed")
+        if data is not None:
+            rc = self._L.pinn_device_upload(self.ptr, data.ctypes.data_as(C.c_void_p), data.nbytes, None)
+            if rc:
+                raise PinnError(rc, "pinn_device_upload failed")
+
+    @property
+    def code(self):
+        return 0 if self.dtype == np.dtype(np.float32) else 1
+
+    def numpy(self):
+        out = np.empty(self.n, dtype=self.dtype)
+        rc = self._L.pinn_device_download(out.ctypes.data_as(C.c_void_p), self.ptr, out.nbytes, None)
+        if rc:
+            raise PinnError(rc, "pinn_device_download failed")
+        return out
+
+    def free(self):
+        if self.ptr:
+            self._L.pinn_device_free(self.ptr, None)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def tensor_elementwise(op, a, b, exact_bounds=True):
+    """r = a (op) b with the reference's flat-index broadcast; returns (status, DeviceArray)."""
+    r = DeviceArray(n=max(a.n, b.n), dtype=a.dtype)
+    rc = lib().pinn_tensor_elementwise(op, a.code, a.ptr, a.n, b.ptr, b.n, r.ptr, r.n, 1 if exact_bounds else 0, None)
+    return rc, r
+
+
+def tensor_matmul(a, b, I, K, J, a_transposed=False, b_transposed=False):
+    r = DeviceArray(n=I * J, dtype=a.dtype)
+    rc = lib().pinn_tensor_matmul(a.code, a.ptr, int(a_transposed), b.ptr, int(b_transposed), r.ptr, I, K, J, None)
+    if rc:
+        raise PinnError(rc, "pinn_tensor_matmul failed")
+    return r
+
+
+def tensor_dot(a, b):
+    r = DeviceArray(n=1, dtype=a.dtype)
+    rc = lib().pinn_tensor_dot(a.code, a.ptr, b.ptr, a.n, r.ptr, None, None)
+    if rc:
+        raise PinnError(rc, "pinn_tensor_dot failed")
+    return r
+
+
+def tensor_add_multiple(srcs):
+    r = DeviceArray(n=srcs[0].n, dtype=srcs[0].dtype)
+    arr = (C.c_void_p * len(srcs))(*[s.ptr for s in srcs])
+    rc = lib().pinn_tensor_add_multiple(srcs[0].code, arr, len(srcs), srcs[0].n, r.ptr, None)
+    if rc:
+        raise PinnError(rc, "pinn_tensor_add_multiple failed")
+    return r

@@ -6,9 +6,9 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libpinn_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", "pinn_capi.cu")]
+SOURCES = [os.path.join(HERE, "csrc", "pinn_capi.cu"), os.path.join(HERE, "csrc", "pinn_tensor_ops.cu")]
 DEPS = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + \
-       [os.path.join(ROOT, "include", "pinn_abi.h")]
+       [os.path.join(ROOT, "include", "pinn_abi.h"), os.path.join(ROOT, "include", "pinn_tensor_abi.h")]
 
 
 def nvcc_path():

@@ -770,9 +770,9 @@ static int configure_kernels(pinn_ctx* c) {
                 int coop = 0;
                 CUDA_TRY(c, "pinn_create", cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->cfg.device));
                 if (coop && nprod >= 8 && smem2 <= max_smem) {
-                    // default producer: two sub-tiles in flight (pinn_fused_tc3.cuh); PINN_TC3=0 keeps the one-tile producer of tc2
+                    // PINN_TC3=1: the experimental producer with two sub-tiles in flight (pinn_fused_tc3.cuh; measured no faster)
                     const char* e3 = getenv("PINN_TC3");
-                    const bool tc3on = !(e3 && atoi(e3) == 0);
+                    const bool tc3on = e3 && atoi(e3) != 0;
                     if (tc3on) { c->kern_tc2 = H == 128 ? fused_step_tc3<3, 2, 128> : fused_step_tc3<3, 2, 256>; c->tc2_T = tc3::T; c->tc2_threads = 2 * H + tc3::kHelperThreads; }
                     else { c->kern_tc2 = H == 128 ? fused_step_tc2<3, 2, 128> : fused_step_tc2<3, 2, 256>; c->tc2_T = tc2::T; c->tc2_threads = 2 * H; }
                     CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
@@ -912,6 +912,7 @@ static int launch_tc2(pinn_ctx* c, const PointSet& interior, int* rows_out) {
     a.ready = c->d_tc2_flags; a.done = c->d_tc2_flags + (size_t)c->tc2_nprod * kFlagStride;
     a.stagger = 4;
     if (const char* es = getenv("PINN_TC3_STAGGER")) a.stagger = atoi(es);
+    if (c->tc2_T != tc3::T) { const char* el = getenv("PINN_TC2_LEAN"); a.stagger = (el && atoi(el) == 0) ? -1 : 0; }
     a.ready2 = c->tc2_T == tc3::T ? c->d_tc2_flags + 2 * (size_t)c->tc2_nprod * kFlagStride : nullptr;
     a.nprod = c->tc2_nprod; a.q = c->tc2_q; a.zdepth = c->tc2_zdepth; a.dbg = c->d_tc2_dbg;
     a.trap_site = reinterpret_cast<int*>(c->d_hrec + 16);

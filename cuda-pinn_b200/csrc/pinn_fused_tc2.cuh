@@ -310,6 +310,10 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
     // the UMMA issue blocks its thread for most of the step: it lives in a warp of the LAST M-tile, which waits for the end of the step anyway
     const int kIssuer = MT == 2 ? 160 : 0;
+    // the issuer's WARP enters issue_step as a whole (warp-uniform branch) and one elected lane issues: with a `tid == k` branch the
+    // compiler wraps every tcgen05.mma in an ELECT loop and rebuilds both descriptors — ~16 SASS instructions and ~94 cycles per UMMA
+    // from a single thread, against 69 of execution
+    const bool issuer_warp = __shfl_sync(0xffffffffu, warp, 0) == kIssuer / 32;
 
     if (warp == 0) umma::tmem_alloc(&tmem_slot, 512u);
     if (tid == 0) {
@@ -364,7 +368,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     // ---- weight slabs (thread 0): step sc of the per-tile schedule  fwd l = 2..L, then reverse l = L..2 ----
     const long long nsteps = (long long)my_tiles * 2 * (L - 1);
     auto slab_src = [&](long long s_, int m) -> const __nv_bfloat16* {
-        const int idx = (int)(s_ % (2 * (L - 1)));
+        const int idx = (int)((unsigned)s_ % (unsigned)(2 * (L - 1)));   // (32-bit: a 64-bit modulo here was 9 % of the kernel's instructions)
         const bool fwd = idx < L - 1;
         const int l = fwd ? 2 + idx : L - (idx - (L - 1));
         return (fwd ? ta.wf : ta.wb) + ((size_t)(l - 2) * MT + m) * (size_t)(128 * H);
@@ -516,21 +520,31 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     };
     // forward / reverse UMMAs of step s_ (thread 0): M-tile m as soon as its weight slab has landed; after the last UMMA of
     // M-tile 0 a commit on slab_free lets the loader thread refill that buffer while M-tile 1 still runs.
-    auto issue_step = [&](long long s_, bool fwd) {
+    auto issue_step = [&](long long s_, bool fwd) {               // (all lanes of the issuer's warp)
         #pragma unroll
         for (int m = 0; m < MT; m++) {
             mbar_wait_at(&wbar[slab_buf(s_, m)], slab_phase(s_), ta.trap_site, 105);
             umma::tc_fence_after();
-            if (fwd)       // A = W_l^T slab (MN-major: 8-unit groups CHS apart, 8 k rows 128 B apart)
-                umma::gemm_issue(tmem + (uint32_t)(m * 128), w_addr + (uint32_t)slab_buf(s_, m) * SLAB, 128, CHS, 256,
-                                 op_addr, 128, CHS, 256, umma::idesc_bf16(128, 128, 1, 1), H / 16, 0u);
-            else           // A = W_l rows (K-major: 8-unit chunks of j 2048 B apart, 8 k rows 128 B apart)
-                umma::gemm_issue(tmem + (uint32_t)(m * 128), w_addr + (uint32_t)slab_buf(s_, m) * SLAB, 2048, 128, 4096,
-                                 op_addr, 128, CHS, 256, umma::idesc_bf16(128, 128, 0, 1), H / 16, 0u);
-            if (MT == 2 && m == 0) { umma::mma_commit(&slab_free); umma::mma_commit(&m0_bar); }
+            if (ta.stagger < 0 ? lane == 0 : umma::elect_one()) {
+                if (ta.stagger < 0) {      // (A/B switch for measurements, PINN_TC2_LEAN=0: the descriptor-per-UMMA issue of round 1)
+                    if (fwd) umma::gemm_issue(tmem + (uint32_t)(m * 128), w_addr + (uint32_t)slab_buf(s_, m) * SLAB, 128, CHS, 256,
+                                              op_addr, 128, CHS, 256, umma::idesc_bf16(128, 128, 1, 1), H / 16, 0u);
+                    else umma::gemm_issue(tmem + (uint32_t)(m * 128), w_addr + (uint32_t)slab_buf(s_, m) * SLAB, 2048, 128, 4096,
+                                          op_addr, 128, CHS, 256, umma::idesc_bf16(128, 128, 0, 1), H / 16, 0u);
+                } else if (fwd)   // A = W_l^T slab (MN-major: 8-unit groups CHS apart, 8 k rows 128 B apart)
+                    umma::gemm_issue_lean<H / 16>(tmem + (uint32_t)(m * 128), w_addr + (uint32_t)slab_buf(s_, m) * SLAB, 128, CHS, 256,
+                                                  op_addr, 128, CHS, 256, umma::idesc_bf16(128, 128, 1, 1), 0u);
+                else       // A = W_l rows (K-major: 8-unit chunks of j 2048 B apart, 8 k rows 128 B apart)
+                    umma::gemm_issue_lean<H / 16>(tmem + (uint32_t)(m * 128), w_addr + (uint32_t)slab_buf(s_, m) * SLAB, 2048, 128, 4096,
+                                                  op_addr, 128, CHS, 256, umma::idesc_bf16(128, 128, 0, 1), 0u);
+                if (MT == 2 && m == 0) { umma::mma_commit(&slab_free); umma::mma_commit(&m0_bar); }
+                if (m == MT - 1) {
+                    umma::mma_commit(&mma_bar);
+                    if (MT == 1) request_step(s_ + 1);
+                }
+            }
+            __syncwarp();
         }
-        umma::mma_commit(&mma_bar);
-        if (MT == 1) request_step(s_ + 1);
     };
     uint32_t free_phase = 0;                         // loader thread (tid 32), MT == 2
     // loader thread: next step's slab for buffer 0 as soon as M-tile 0 is done, for buffer 1 when the whole step is
@@ -593,7 +607,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
         uint8_t* lo_img = Wb0;                       // bf16 remainder of A_L: in a weight buffer that is idle around the output layer
         for (int l = 2; l <= L; l++, sc++) {
             const long long c_a = dbg ? clock64() : 0;
-            if (tid == kIssuer) issue_step(sc, true);
+            if (issuer_warp) issue_step(sc, true);
             if (tid == kWaiter) {
                 if (l < L && t > 0) wait_ge_at(dn + (l + 1), (unsigned)t, ta.trap_site, 114);   // A_l of the previous tile may be overwritten
                 if (MT == 2) mbar_arrive(&m0_bar);
@@ -640,13 +654,16 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
 
         // ---------------- output layer on the tensor cores: y[n, :] = (A_L hi + lo)^T[n, k] . [W_{L+1} hi | lo][k, :] ----------------
         const long long c_o = dbg ? clock64() : 0;
-        if (tid == kIssuer) {
+        if (issuer_warp) {
             umma::tc_fence_after();
-            umma::gemm_issue(tmem + OUTCOL, op_addr, 128, CHS, 256, umma::smem_u32(wo16), 128, CHS, 256,
-                             umma::idesc_bf16(128, 16, 1, 1), H / 16, 0u);
-            umma::gemm_issue(tmem + OUTCOL, umma::smem_u32(lo_img), 128, CHS, 256, umma::smem_u32(wo16), 128, CHS, 256,
-                             umma::idesc_bf16(128, 16, 1, 1), H / 16, 1u);
-            umma::mma_commit(&out_bar);
+            if (umma::elect_one()) {
+                umma::gemm_issue_lean<H / 16>(tmem + OUTCOL, op_addr, 128, CHS, 256, umma::smem_u32(wo16), 128, CHS, 256,
+                                              umma::idesc_bf16(128, 16, 1, 1), 0u);
+                umma::gemm_issue_lean<H / 16>(tmem + OUTCOL, umma::smem_u32(lo_img), 128, CHS, 256, umma::smem_u32(wo16), 128, CHS, 256,
+                                              umma::idesc_bf16(128, 16, 1, 1), 1u);
+                umma::mma_commit(&out_bar);
+            }
+            __syncwarp();
         }
         mbar_wait_at(&out_bar, out_phase, ta.trap_site, 109); out_phase ^= 1;
         umma::tc_fence_after();
@@ -782,7 +799,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
             umma::tc_fence_before();
             __syncthreads();
             const long long c_f = dbg ? clock64() : 0;
-            if (tid == kIssuer) issue_step(sc, false);
+            if (issuer_warp) issue_step(sc, false);
             if (tid == kPublisher) {                     // Zbar_l (and, since the forward pass, A_{l-1}) are in memory
                 __threadfence();
                 st_release(rdy + l, (unsigned)t + 1u);

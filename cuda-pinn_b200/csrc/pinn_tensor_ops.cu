@@ -1,0 +1,306 @@
+// pinn_tensor_ops.cu — B200-native device arithmetic of the reference's tensor<T> (include/pinn_tensor_abi.h): elementwise
+// add / sub / mul / div with the reference's flat-index broadcast, row-major matmul, dot, variadic add; device-resident,
+// stream-ordered.  These are HBM-bound (elementwise, dot: 8-12 B per element) or small FP32 contractions whose results must
+// equal the reference's bit for bit, so: coalesced 16-byte accesses, grids sized to the SM count, a shared-memory tiled
+// CUDA-core matmul that keeps the reference's per-element operation order (one accumulator, k ascending, fused
+// multiply-add — kernel.cuh:77-80 as nvcc compiles it) — no tensor cores, which would change the rounding.
+// Replaces: include/device/kernel.cuh:10-99 and the host sequences around them in include/tensor.cuh:84-140, 347-508.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "../../include/pinn_tensor_abi.h"
+
+namespace {
+
+int g_sms = 0;
+int sm_count() {
+    if (g_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_sms = 148;
+    }
+    return g_sms;
+}
+
+template <typename T, int OP>
+__device__ __forceinline__ T apply(T a, T b) {
+    if (OP == PINN_OP_ADD) return a + b;
+    if (OP == PINN_OP_SUB) return a - b;
+    if (OP == PINN_OP_MUL) return a * b;
+    return a / b;
+}
+
+// same-size operands (the common case): 16-byte accesses, grid-stride
+template <typename T, int OP>
+__global__ void elementwise_same(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ r, size_t n, int* __restrict__ flag) {
+    constexpr int V = 16 / sizeof(T);
+    struct alignas(16) Vec { T v[V]; };
+    const size_t nv = n / V, stride = (size_t)gridDim.x * blockDim.x;
+    bool zero = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const Vec x = reinterpret_cast<const Vec*>(a)[i], y = reinterpret_cast<const Vec*>(b)[i];
+        Vec z = reinterpret_cast<Vec*>(r)[i];                                  // (div: a zero denominator leaves the element as it was)
+        #pragma unroll
+        for (int k = 0; k < V; k++) {
+            if (OP == PINN_OP_DIV && y.v[k] == T(0)) zero = true;
+            else z.v[k] = apply<T, OP>(x.v[k], y.v[k]);
+        }
+        reinterpret_cast<Vec*>(r)[i] = z;
+    }
+    for (size_t i = nv * V + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (OP == PINN_OP_DIV && b[i] == T(0)) zero = true;
+        else r[i] = apply<T, OP>(a[i], b[i]);
+    }
+    if (OP == PINN_OP_DIV && zero) atomicExch(flag, 1);
+}
+
+// the reference's broadcast: flat index modulo the operand size (kernel.cuh:16)
+template <typename T, int OP>
+__global__ void elementwise_bcast(const T* __restrict__ a, size_t na, const T* __restrict__ b, size_t nb, T* __restrict__ r, size_t bound,
+                                  int* __restrict__ flag) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    bool zero = false;
+    const bool small = na < (1ull << 32) && nb < (1ull << 32) && bound < (1ull << 32);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bound; i += stride) {
+        const size_t ia = small ? (size_t)((uint32_t)i % (uint32_t)na) : i % na, ib = small ? (size_t)((uint32_t)i % (uint32_t)nb) : i % nb;
+        const T y = b[ib];
+        if (OP == PINN_OP_DIV && y == T(0)) zero = true;
+        else r[i] = apply<T, OP>(a[ia], y);
+    }
+    if (OP == PINN_OP_DIV && zero) atomicExch(flag, 1);
+}
+
+// R[I, J] = A[I, K] B[K, J]: 64 x 64 output tile per CTA, 4 x 4 per thread, K in slices of 16 through shared memory.
+// Every output keeps ONE accumulator and takes its products in ascending k with fma — the reference's order.
+template <typename T, bool TA, bool TB>
+__global__ void __launch_bounds__(256) matmul_tiled(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ R, size_t I, size_t K, size_t J) {
+    constexpr int TM = 64, TN = 64, TK = 16;
+    __shared__ T As[TK][TM + 4];
+    __shared__ T Bs[TK][TN + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;                 // tx: 4 columns, ty: 4 rows
+    const size_t i0 = (size_t)blockIdx.y * TM, j0 = (size_t)blockIdx.x * TN;
+    T acc[4][4];
+    #pragma unroll
+    for (int a = 0; a < 4; a++)
+        #pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = T(0);
+    for (size_t k0 = 0; k0 < K; k0 += TK) {
+        const int kmax = (int)((K - k0) < (size_t)TK ? (K - k0) : (size_t)TK);
+        // A slice -> As[k][i] (coalesced along the stored-contiguous index)
+        for (int e = threadIdx.x; e < TM * TK; e += 256) {
+            int k, i;
+            if (TA) { i = e % TM; k = e / TM; } else { k = e % TK; i = e / TK; }
+            const size_t gi = i0 + i, gk = k0 + k;
+            T v = T(0);
+            if (gi < I && gk < K) v = TA ? A[gk * I + gi] : A[gi * K + gk];
+            As[k][i] = v;
+        }
+        for (int e = threadIdx.x; e < TN * TK; e += 256) {
+            int k, j;
+            if (TB) { k = e % TK; j = e / TK; } else { j = e % TN; k = e / TN; }
+            const size_t gj = j0 + j, gk = k0 + k;
+            T v = T(0);
+            if (gj < J && gk < K) v = TB ? B[gj * K + gk] : B[gk * J + gj];
+            Bs[k][j] = v;
+        }
+        __syncthreads();
+        for (int k = 0; k < kmax; k++) {                                       // (exact bound: no padded products, the sign of a zero sum is the reference's)
+            T a[4], b[4];
+            #pragma unroll
+            for (int u = 0; u < 4; u++) { a[u] = As[k][ty * 4 + u]; b[u] = Bs[k][tx * 4 + u]; }
+            #pragma unroll
+            for (int u = 0; u < 4; u++)
+                #pragma unroll
+                for (int v = 0; v < 4; v++) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+        }
+        __syncthreads();
+    }
+    #pragma unroll
+    for (int u = 0; u < 4; u++)
+        #pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const size_t gi = i0 + ty * 4 + u, gj = j0 + tx * 4 + v;
+            if (gi < I && gj < J) R[gi * J + gj] = acc[u][v];
+        }
+}
+
+// dot, stage 1: fixed assignment of elements to threads, shuffle tree, shared-memory tree -> one partial per CTA
+template <typename T>
+__global__ void __launch_bounds__(256) dot_partial(const T* __restrict__ a, const T* __restrict__ b, size_t n, T* __restrict__ partial) {
+    __shared__ T warp_sum[8];
+    T s = T(0);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) s = fma(a[i], b[i], s);
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T t = T(0);
+        #pragma unroll
+        for (int w = 0; w < 8; w++) t += warp_sum[w];
+        partial[blockIdx.x] = t;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) dot_final(const T* __restrict__ partial, int count, T* __restrict__ r) {
+    __shared__ T warp_sum[8];
+    T s = T(0);
+    for (int i = threadIdx.x; i < count; i += 256) s += partial[i];
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T t = T(0);
+        #pragma unroll
+        for (int w = 0; w < 8; w++) t += warp_sum[w];
+        r[0] = t;
+    }
+}
+
+struct SrcList { const void* p[16]; };
+template <typename T>
+__global__ void add_multiple_kernel(const SrcList srcs, int count, size_t n, T* __restrict__ r) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T sum = T(0);
+        for (int k = 0; k < count; k++) sum += static_cast<const T*>(srcs.p[k])[i];     // (the reference's order, kernel.cuh:61-63)
+        r[i] = sum;
+    }
+}
+
+int grid_for(size_t n, int per_thread) {
+    const size_t want = (n + (size_t)256 * per_thread - 1) / ((size_t)256 * per_thread);
+    const size_t cap = (size_t)sm_count() * 8;                                  // a multiple of the SM count; grid-stride loops take the rest
+    return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+template <typename T, int OP>
+int run_elementwise(const T* a, size_t na, const T* b, size_t nb, T* r, size_t nr, int exact_bounds, cudaStream_t st) {
+    int* flag = nullptr;
+    if (OP == PINN_OP_DIV) {
+        if (cudaMallocAsync(&flag, sizeof(int), st) != cudaSuccess || cudaMemsetAsync(flag, 0, sizeof(int), st) != cudaSuccess) return PINN_ERR_CUDA;
+    }
+    const size_t bound = ((OP == PINN_OP_MUL || OP == PINN_OP_DIV) && exact_bounds) ? (na < nr ? na : nr) : nr;
+    const bool aligned = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)r) & 15) == 0;
+    if (bound > 0) {
+        if (na == nb && na == nr && aligned) elementwise_same<T, OP><<<grid_for(nr, 16 / sizeof(T) * 2), 256, 0, st>>>(a, b, r, nr, flag);
+        else elementwise_bcast<T, OP><<<grid_for(bound, 4), 256, 0, st>>>(a, na, b, nb, r, bound, flag);
+    }
+    if (cudaGetLastError() != cudaSuccess) return PINN_ERR_CUDA;
+    if (OP == PINN_OP_DIV) {
+        int h = 0;
+        if (cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return PINN_ERR_CUDA;
+        cudaFreeAsync(flag, st);
+        if (h) return PINN_ERR_DIVISION_BY_ZERO;
+    }
+    return PINN_OK;
+}
+
+template <typename T>
+int dispatch_elementwise(int op, const void* a, size_t na, const void* b, size_t nb, void* r, size_t nr, int eb, cudaStream_t st) {
+    const T* pa = static_cast<const T*>(a); const T* pb = static_cast<const T*>(b); T* pr = static_cast<T*>(r);
+    switch (op) {
+        case PINN_OP_ADD: return run_elementwise<T, PINN_OP_ADD>(pa, na, pb, nb, pr, nr, eb, st);
+        case PINN_OP_SUB: return run_elementwise<T, PINN_OP_SUB>(pa, na, pb, nb, pr, nr, eb, st);
+        case PINN_OP_MUL: return run_elementwise<T, PINN_OP_MUL>(pa, na, pb, nb, pr, nr, eb, st);
+        case PINN_OP_DIV: return run_elementwise<T, PINN_OP_DIV>(pa, na, pb, nb, pr, nr, eb, st);
+    }
+    return PINN_ERR_INVALID_ARGUMENT;
+}
+
+template <typename T>
+int run_matmul(const T* a, int ta, const T* b, int tb, T* r, size_t I, size_t K, size_t J, cudaStream_t st) {
+    const dim3 grid((unsigned)((J + 63) / 64), (unsigned)((I + 63) / 64));
+    if (ta && tb) matmul_tiled<T, true, true><<<grid, 256, 0, st>>>(a, b, r, I, K, J);
+    else if (ta) matmul_tiled<T, true, false><<<grid, 256, 0, st>>>(a, b, r, I, K, J);
+    else if (tb) matmul_tiled<T, false, true><<<grid, 256, 0, st>>>(a, b, r, I, K, J);
+    else matmul_tiled<T, false, false><<<grid, 256, 0, st>>>(a, b, r, I, K, J);
+    return cudaGetLastError() == cudaSuccess ? PINN_OK : PINN_ERR_CUDA;
+}
+
+template <typename T>
+int run_dot(const T* a, const T* b, size_t n, T* r, T* scratch, cudaStream_t st) {
+    const int blocks = (int)pinn_tensor_dot_scratch(n);
+    T* part = scratch;
+    if (!part && cudaMallocAsync(&part, (size_t)blocks * sizeof(T), st) != cudaSuccess) return PINN_ERR_CUDA;
+    dot_partial<T><<<blocks, 256, 0, st>>>(a, b, n, part);
+    dot_final<T><<<1, 256, 0, st>>>(part, blocks, r);
+    const bool ok = cudaGetLastError() == cudaSuccess;
+    if (!scratch) cudaFreeAsync(part, st);
+    return ok ? PINN_OK : PINN_ERR_CUDA;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pinn_tensor_elementwise(int op, int dtype, const void* a, size_t na, const void* b, size_t nb, void* r, size_t nr, int exact_bounds, void* stream) {
+    if (!a || !b || !r || na == 0 || nb == 0 || nr != (na > nb ? na : nb) || op < 0 || op > 3) return PINN_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == 0) return dispatch_elementwise<float>(op, a, na, b, nb, r, nr, exact_bounds, st);
+    if (dtype == 1) return dispatch_elementwise<double>(op, a, na, b, nb, r, nr, exact_bounds, st);
+    return PINN_ERR_INVALID_ARGUMENT;
+}
+
+int pinn_tensor_matmul(int dtype, const void* a, int a_transposed, const void* b, int b_transposed, void* r, size_t I, size_t K, size_t J, void* stream) {
+    if (!a || !b || !r || I == 0 || K == 0 || J == 0) return PINN_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == 0) return run_matmul<float>(static_cast<const float*>(a), a_transposed, static_cast<const float*>(b), b_transposed, static_cast<float*>(r), I, K, J, st);
+    if (dtype == 1) return run_matmul<double>(static_cast<const double*>(a), a_transposed, static_cast<const double*>(b), b_transposed, static_cast<double*>(r), I, K, J, st);
+    return PINN_ERR_INVALID_ARGUMENT;
+}
+
+size_t pinn_tensor_dot_scratch(size_t n) {
+    const size_t want = (n + 256 * 8 - 1) / (256 * 8);
+    const size_t cap = (size_t)sm_count() * 4;
+    return want < 1 ? 1 : (want > cap ? cap : want);
+}
+
+int pinn_tensor_dot(int dtype, const void* a, const void* b, size_t n, void* r, void* scratch, void* stream) {
+    if (!a || !b || !r || n == 0) return PINN_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == 0) return run_dot<float>(static_cast<const float*>(a), static_cast<const float*>(b), n, static_cast<float*>(r), static_cast<float*>(scratch), st);
+    if (dtype == 1) return run_dot<double>(static_cast<const double*>(a), static_cast<const double*>(b), n, static_cast<double*>(r), static_cast<double*>(scratch), st);
+    return PINN_ERR_INVALID_ARGUMENT;
+}
+
+int pinn_tensor_add_multiple(int dtype, const void* const* srcs, size_t count, size_t n, void* r, void* stream) {
+    if (!srcs || !r || count == 0 || count > 16 || n == 0) return PINN_ERR_INVALID_ARGUMENT;
+    SrcList l{};
+    for (size_t k = 0; k < count; k++) { if (!srcs[k]) return PINN_ERR_INVALID_ARGUMENT; l.p[k] = srcs[k]; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == 0) add_multiple_kernel<float><<<grid_for(n, 4), 256, 0, st>>>(l, (int)count, n, static_cast<float*>(r));
+    else if (dtype == 1) add_multiple_kernel<double><<<grid_for(n, 4), 256, 0, st>>>(l, (int)count, n, static_cast<double*>(r));
+    else return PINN_ERR_INVALID_ARGUMENT;
+    return cudaGetLastError() == cudaSuccess ? PINN_OK : PINN_ERR_CUDA;
+}
+
+int pinn_device_alloc(void** ptr, size_t bytes, void* stream) {
+    if (!ptr || bytes == 0) return PINN_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cudaMallocAsync(ptr, bytes, st) != cudaSuccess) return PINN_ERR_CUDA;
+    return cudaMemsetAsync(*ptr, 0, bytes, st) == cudaSuccess ? PINN_OK : PINN_ERR_CUDA;   // (the reference zero-fills new tensors, interface.cuh:99-103)
+}
+int pinn_device_free(void* ptr, void* stream) {
+    if (!ptr) return PINN_OK;
+    return cudaFreeAsync(ptr, static_cast<cudaStream_t>(stream)) == cudaSuccess ? PINN_OK : PINN_ERR_CUDA;
+}
+int pinn_device_upload(void* dst, const void* host_src, size_t bytes, void* stream) {
+    if (!dst || !host_src) return PINN_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cudaMemcpyAsync(dst, host_src, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return PINN_ERR_CUDA;
+    return cudaStreamSynchronize(st) == cudaSuccess ? PINN_OK : PINN_ERR_CUDA;
+}
+int pinn_device_download(void* host_dst, const void* src, size_t bytes, void* stream) {
+    if (!host_dst || !src) return PINN_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cudaMemcpyAsync(host_dst, src, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return PINN_ERR_CUDA;
+    return cudaStreamSynchronize(st) == cudaSuccess ? PINN_OK : PINN_ERR_CUDA;
+}
+
+int pinn_device_copy(void* dst, const void* src, size_t bytes, void* stream) {
+    if (!dst || !src) return PINN_ERR_INVALID_ARGUMENT;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)) == cudaSuccess ? PINN_OK : PINN_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -33,6 +33,23 @@ def test_library_exports_every_declared_symbol(P):
     assert sorted(P.ABI_SYMBOLS) == declared, "python binding and header disagree on the ABI surface"
 
 
+def test_library_exports_the_tensor_abi(P):
+    """include/pinn_tensor_abi.h: every declared entry point is exported, and argument checks that need no GPU answer
+    PINN_ERR_INVALID_ARGUMENT (no compute call is made here)."""
+    src = open(os.path.join(ROOT, "include", "pinn_tensor_abi.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(pinn_[a-z_0-9]+)\s*\(", src)))
+    assert declared == ["pinn_device_alloc", "pinn_device_copy", "pinn_device_download", "pinn_device_free", "pinn_device_upload",
+                        "pinn_tensor_add_multiple", "pinn_tensor_dot", "pinn_tensor_dot_scratch", "pinn_tensor_elementwise", "pinn_tensor_matmul"]
+    L = P.lib()
+    for name in declared:
+        assert hasattr(L, name), f"libpinn_b200.so does not export {name}"
+    assert L.pinn_tensor_elementwise(0, 0, None, 4, None, 4, None, 4, 1, None) == 3       # null pointers
+    assert L.pinn_tensor_matmul(0, None, 0, None, 0, None, 2, 2, 2, None) == 3
+    assert L.pinn_tensor_dot(0, None, None, 8, None, None, None) == 3
+    assert L.pinn_device_alloc(None, 16, None) == 3
+
+
 def test_config_struct_layout_matches_oracle_mirror(P, oracle):
     assert C.sizeof(P.PinnConfig) == C.sizeof(oracle.PinnConfig) == 128
     assert [f[0] for f in P.PinnConfig._fields_] == [f[0] for f in oracle.PinnConfig._fields_]
