@@ -81,7 +81,8 @@ class device_tensor {
 
         // upload a reference tensor's host copy (raw() is authoritative in the reference)
         explicit device_tensor(const tensor<T> &t, void *stream_ = nullptr): stream{stream_} {
-            this->allocate(t.get_shape().empty()? std::vector<size_t>{1}: std::vector<size_t>(t.get_shape().begin(), t.get_shape().end()));
+            const std::vector<size_t> sh = t.get_shape();            // (by value in the reference: init_tensor.h:305)
+            this->allocate(sh.empty()? std::vector<size_t>{1}: sh);
             device_tensor::check(pinn_device_upload(this->data, t.raw(), this->n * sizeof(T), this->stream), "upload");
         }
 

@@ -8,8 +8,12 @@ top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "cuda-pinn_b200", "libpinn_b200.so")], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
+sass = []
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):      # one cubin per source file of the library
+    text = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
+    if any(l.startswith(".text.") and sub in l for l in text):
+        sass = text
+        break
 start = [i for i, l in enumerate(sass) if l.startswith(".text.") and sub in l][0]
 cur, ins = None, []
 for l in sass[start + 1:]:
