@@ -21,7 +21,6 @@
 #include "pinn_fused_tc.cuh"
 #include "pinn_fused_tc2.cuh"
 #include "pinn_fused_tc3.cuh"
-#include "pinn_fused_warp.cuh"
 #include "pinn_fused_mma.cuh"
 
 using namespace pinn;
@@ -445,8 +444,7 @@ struct pinn_ctx {
     float* d_hrec = nullptr;            // device address of h_pinned
     const float* x_override = nullptr;  // pinn_train_step_host: device-mapped address of the caller's pinned interior points
     // launch configuration of the fused kernels
-    fused_fn kern_full = nullptr, kern_val = nullptr, kern_warp = nullptr;   // kern_warp: warp-autonomous narrow-net kernel
-    int warp_wpc = 6, warp_smem = 0;
+    fused_fn kern_full = nullptr, kern_val = nullptr;
     int TP = 32, UT = 4, threads = 0, smem_full = 0, smem_val = 0, grid_cap_full = 0, grid_cap_val = 0;
     int val_TP = 32, val_UT = 4, val_threads = 0;   // value-only (boundary / initial / pinn_forward) launch shape
     int rows_cap_a = 0, rows_cap_b = 0, nsplit_cap = 1, kernel_id = 0, num_sms = 148;
@@ -675,21 +673,6 @@ static int configure_kernels(pinn_ctx* c) {
     c->grid_cap_full = occ_f * c->num_sms;
     c->grid_cap_val = occ_v * c->num_sms;
     c->kernel_id = (c->UT == 8 ? 10 : 0) + (c->TP == 16 ? 1 : 0);
-    // warp-autonomous kernel for the headline narrow network (Burgers 2 -> [20 x L] -> 1), training launches only
-    // Opt-in (PINN_WARP_KERNEL=1): measured on B200 it matches the block-tile kernel on C2 (125 vs 131 us) but its
-    // 217 KB of shared memory keeps the concurrent boundary/initial launch off the SMs (step 193 vs 146 us).
-    if (c->cfg.precision == PINN_PREC_FP32 && H == 20 && nd.d_in == 2 && nd.n2 == 1 && getenv("PINN_WARP_KERNEL")) {
-        c->kern_warp = fused_step_warp<2, 1, 20, 6>;
-        c->warp_wpc = 6;
-        const int P4 = (nd.P + 3) & ~3;
-        c->warp_smem = (2 * P4 + c->warp_wpc * (3 * H + 1) * (nd.C * 32 + 4)) * (int)sizeof(float);
-        if (c->warp_smem <= max_smem) {
-            CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, c->warp_smem));
-            c->kernel_id = 50;
-        } else {
-            c->kern_warp = nullptr;
-        }
-    }
     // kernels of one step run concurrently (interior || boundary/initial): give them the SAME shared-memory carve-out, or an
     // SM configured for one cannot take CTAs of the other until it drains (measured: the value launch serialised, +30 us)
     CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_full, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -841,13 +824,9 @@ static int launch_fused(pinn_ctx* c, cudaStream_t stream, bool full, const Point
         total = 0;
         for (int i = 0; i < nsets; i++) { a.sets[i].ntiles = tiles_of(a.sets[i].n, tcv ? 128 : 16); total += a.sets[i].ntiles; }
     }
-    const bool wk = full && mode == 0 && !tc && c->kern_warp != nullptr;
     const int cap = tc ? c->grid_cap_tc : (full ? c->grid_cap_full : c->grid_cap_val);
     (void)tcv;
     int grid = total < cap ? total : cap;
-    if (wk) {                                             // one warp per 32-point tile, WPC warps per CTA, one CTA per SM
-        grid = total < c->num_sms ? total : c->num_sms;        // spread tiles over the SMs first, then over warps
-    }
     const bool timed = c->prof && full && mode == 0 && !c->capturing;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {
@@ -859,15 +838,13 @@ static int launch_fused(pinn_ctx* c, cudaStream_t stream, bool full, const Point
         ta.f = a; ta.wq = c->d_wq; ta.wq_term_stride = c->wq_term_stride; ta.tmem_cols = c->tc_tmem_cols;
         ta.op_ring = c->d_ring; ta.ring_per_cta = c->ring_per_cta; ta.defer_g = (mode == 0 && !tcv) ? c->tc_defer_g : 0;
         (tcv ? c->kern_tc_val : c->kern_tc)<<<grid, c->tc_threads, c->tc_smem, stream>>>(c->nd, ta);
-    } else if (wk) {
-        c->kern_warp<<<grid, c->warp_wpc * 32, c->warp_smem, stream>>>(c->nd, a);
     } else {
         if (full) c->kern_full<<<grid, c->threads, c->smem_full, stream>>>(c->nd, a);
         else c->kern_val<<<grid, c->val_threads, c->smem_val, stream>>>(c->nd, a);
     }
     if (timed) { cudaEventRecord(e1, stream); c->pending.emplace_back(e0, e1); }
     if (full) c->last_grid = grid;
-    if (grid_out) *grid_out = wk ? grid * c->warp_wpc : grid;   // partial rows this launch used
+    if (grid_out) *grid_out = grid;                       // partial rows this launch used
     c->step_launches++;
     CUDA_TRY(c, "pinn_train_step", cudaGetLastError());
     return PINN_OK;
@@ -911,6 +888,7 @@ static int launch_tc2(pinn_ctx* c, const PointSet& interior, int* rows_out) {
     a.wf = c->d_wf; a.wb = c->d_wb; a.stash_a = c->d_st_a; a.stash_s = c->d_st_s; a.zring = c->d_zring;
     a.ready = c->d_tc2_flags; a.done = c->d_tc2_flags + (size_t)c->tc2_nprod * kFlagStride;
     a.stagger = 4;
+    { const char* eb = getenv("PINN_TC2_BULK"); a.bulk_store = (eb && atoi(eb) != 0) ? 1 : 0; }
     if (const char* es = getenv("PINN_TC3_STAGGER")) a.stagger = atoi(es);
     if (c->tc2_T != tc3::T) { const char* el = getenv("PINN_TC2_LEAN"); a.stagger = (el && atoi(el) == 0) ? -1 : 0; }
     a.ready2 = c->tc2_T == tc3::T ? c->d_tc2_flags + 2 * (size_t)c->tc2_nprod * kFlagStride : nullptr;
@@ -1231,7 +1209,6 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     // evaluation calls), [rows_cap_a, rows_cap_a + rows_cap_b) the concurrent boundary/initial launch
     c->rows_cap_a = c->grid_cap_full > c->grid_cap_tc ? c->grid_cap_full : c->grid_cap_tc;
     if (c->grid_cap_val > c->rows_cap_a) c->rows_cap_a = c->grid_cap_val;      // pinn_forward uses the value kernel on rows A
-    if (c->kern_warp && c->num_sms * c->warp_wpc > c->rows_cap_a) c->rows_cap_a = c->num_sms * c->warp_wpc;
     if (c->kern_mma && c->grid_cap_mma * kMmaWarps > c->rows_cap_a) c->rows_cap_a = c->grid_cap_mma * kMmaWarps;
     if (c->kern_tc2 && c->num_sms > c->rows_cap_a) c->rows_cap_a = c->num_sms;
     c->rows_cap_b = c->grid_cap_val > c->grid_cap_tc ? c->grid_cap_val : c->grid_cap_tc;
@@ -1815,8 +1792,8 @@ int pinn_profile_get(pinn_ctx* c, pinn_profile* out, int reset) {
     out->launches = c->launches; out->step_kernel_ms = c->kernel_ms; out->step_kernel_count = c->kernel_count;
     out->grid = c->last_grid;
     // launch shape of the kernel the interior training launch runs (the mma.sync kernel used to report the FP32 kernel's)
-    out->block = c->kern_mma ? kMmaWarps * 32 : (c->kern_tc2 ? c->tc2_threads : (c->kern_tc ? c->tc_threads : (c->kern_warp ? c->warp_wpc * 32 : c->threads)));
-    out->smem_bytes = c->kern_mma ? c->mma_smem : (c->kern_tc2 ? c->tc2_smem : (c->kern_tc ? c->tc_smem : (c->kern_warp ? c->warp_smem : c->smem_full)));
+    out->block = c->kern_mma ? kMmaWarps * 32 : (c->kern_tc2 ? c->tc2_threads : (c->kern_tc ? c->tc_threads : c->threads));
+    out->smem_bytes = c->kern_mma ? c->mma_smem : (c->kern_tc2 ? c->tc2_smem : (c->kern_tc ? c->tc_smem : c->smem_full));
     out->kernel_id = c->kernel_id;
     if (reset) { c->launches = 0; c->kernel_ms = 0.0; c->kernel_count = 0; }
     return PINN_OK;

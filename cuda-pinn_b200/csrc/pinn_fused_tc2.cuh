@@ -50,6 +50,7 @@ struct Tc2Args {
     unsigned int* ready2;          // tc3 only (else null): the same flag for the second sub-tile's half of the images; the server waits for both
     unsigned int* done;            // [nprod][kFlagStride]  done[p][l]  = t+1: server has both operands of tile t on chip
     int nprod, q, zdepth;
+    int bulk_store;                // tc2 (PINN_TC2_BULK=1): stash / ring images leave shared memory by ONE cp.async.bulk per layer instead of 8 x 16-byte st.global per thread
     int stagger;                   // tc3: sub-tile B issues a layer step once A has issued this many of its weight pieces (0 = free-running)
     long long* dbg;                // optional [8]: cycle counters of producer 0 (PINN_TC2_DBG=1), or null
     int* trap_site;                // mapped host memory [4]: {site, block, a, b} of a wait that timed out (see tc2::trap_at)
@@ -400,6 +401,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     const uint32_t tm_row = tmem + lane_addr + (uint32_t)(mt * 128);
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const bool dbg = ta.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    const bool bulk = ta.bulk_store != 0;
     const long long t_begin = clock64();
 
     auto point_ok = [&](int g, int pp) { return G * g + pp < T; };
@@ -595,12 +597,13 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
                     #pragma unroll
                     for (int i = 0; i < N2; i++) z[NC * pp + 1 + DIN + i] = 0.0f;
                 }
-                fwd_group(1, g, z, b1, nullptr, stA + a1_off + (size_t)j * 16);
+                fwd_group(1, g, z, b1, nullptr, bulk ? nullptr : stA + a1_off + (size_t)j * 16);
             }
         }
         umma::fence_async_smem();
         umma::tc_fence_before();
         __syncthreads();
+        if (bulk && tid == kWaiter) { umma::bulk_s2g(stA + a1_off, opA, OPB); umma::bulk_commit(); }
         if (dbg) tacc[6] += clock64() - c_t0;
 
         // ---------------- hidden layers 2..L: tensor cores ----------------
@@ -609,6 +612,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
             const long long c_a = dbg ? clock64() : 0;
             if (issuer_warp) issue_step(sc, true);
             if (tid == kWaiter) {
+                if (bulk) umma::bulk_wait_read_all();    // the bulk store of the previous image has read the operand buffer
                 if (l < L && t > 0) wait_ge_at(dn + (l + 1), (unsigned)t, ta.trap_site, 114);   // A_l of the previous tile may be overwritten
                 if (MT == 2) mbar_arrive(&m0_bar);
                 mbar_arrive(&mma_bar);
@@ -637,7 +641,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
                     #pragma unroll
                     for (int i = 0; i < 24; i++) z[i] = __uint_as_float(rz[gi & 1][i]);
                     fwd_group(l, g0 + gi, z, bl, l == L ? lo_img + (size_t)j * 16 : nullptr,
-                              l < L ? stA + (size_t)(l - 1) * OPB + (size_t)j * 16 : nullptr, early);
+                              (l < L && !bulk) ? stA + (size_t)(l - 1) * OPB + (size_t)j * 16 : nullptr, early);
                 }
             }
             if (early) {
@@ -649,6 +653,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
             umma::fence_async_smem();
             umma::tc_fence_before();
             __syncthreads();
+            if (bulk && l < L && tid == kWaiter) { umma::bulk_s2g(stA + (size_t)(l - 1) * OPB, opA, OPB); umma::bulk_commit(); }
             if (dbg) { const long long c_c = clock64(); tacc[0] += c_b - c_a; tacc[1] += c_c - c_b; }
         }
 
@@ -700,7 +705,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
                 for (int o = 0; o < 3; o++) dbo_acc[o] += ybar[o][0];
             }
         }
-        if (tid == kWaiter) ring_wait(t, L);         // ring slot of Zbar_L
+        if (tid == kWaiter) { if (bulk) umma::bulk_wait_read_all(); ring_wait(t, L); }   // ring slot of Zbar_L
         __syncthreads();
         if (dbg) tacc[2] += clock64() - c_o;
 
@@ -741,7 +746,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
             }
             const long long c_e = dbg ? clock64() : 0;
             float dbsum = 0.0f, dw1[DIN] = {0.0f, 0.0f, 0.0f};
-            uint8_t* const zrow = l > 1 ? ring_row(t, l) : nullptr;
+            uint8_t* const zrow = (l > 1 && !bulk) ? ring_row(t, l) : nullptr;
             #pragma unroll
             for (int gi = 0; gi < 3; gi++) {
                 const int g = g0 + gi;
@@ -800,11 +805,18 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
             __syncthreads();
             const long long c_f = dbg ? clock64() : 0;
             if (issuer_warp) issue_step(sc, false);
-            if (tid == kPublisher) {                     // Zbar_l (and, since the forward pass, A_{l-1}) are in memory
+            if (tid == kPublisher && !bulk) {            // Zbar_l (and, since the forward pass, A_{l-1}) are in memory
                 __threadfence();
                 st_release(rdy + l, (unsigned)t + 1u);
             }
             if (tid == kWaiter) {
+                if (bulk) {                              // the image leaves by one bulk store; publish once it (and every earlier one) has landed
+                    umma::bulk_s2g(ring_row(t, l) - (size_t)j * 16, opA, OPB);
+                    umma::bulk_commit();
+                    umma::bulk_wait_all();
+                    __threadfence();
+                    st_release(rdy + l, (unsigned)t + 1u);
+                }
                 if (l > 2) ring_wait(t, l - 1);          // ring slot of Zbar_{l-1}, written by the next epilogue
                 if (MT == 2) mbar_arrive(&m0_bar);
                 mbar_arrive(&mma_bar);
