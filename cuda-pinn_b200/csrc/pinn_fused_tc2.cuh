@@ -810,12 +810,16 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
                 st_release(rdy + l, (unsigned)t + 1u);
             }
             if (tid == kWaiter) {
-                if (bulk) {                              // the image leaves by one bulk store; publish once it (and every earlier one) has landed
+                if (bulk) {
+                    // the image leaves by one bulk store.  Its completion is not waited for here (this thread's arrival starts every
+                    // epilogue warp): the flag of layer l + 1 is released now that only the newest store can still be in flight, and
+                    // the last two of the tile together
                     umma::bulk_s2g(ring_row(t, l) - (size_t)j * 16, opA, OPB);
                     umma::bulk_commit();
-                    umma::bulk_wait_all();
+                    if (l == 2) umma::bulk_wait_all(); else umma::bulk_wait_all_but_last();
                     __threadfence();
-                    st_release(rdy + l, (unsigned)t + 1u);
+                    if (l < L) st_release(rdy + (l + 1), (unsigned)t + 1u);
+                    if (l == 2) st_release(rdy + 2, (unsigned)t + 1u);
                 }
                 if (l > 2) ring_wait(t, l - 1);          // ring slot of Zbar_{l-1}, written by the next epilogue
                 if (MT == 2) mbar_arrive(&m0_bar);

@@ -57,6 +57,7 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources reusable
+__device__ __forceinline__ void bulk_wait_all_but_last() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }   // every group but the newest has landed
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }             // writes complete
 
 // generic-proxy smem writes -> visible to the async proxy (tensor core / TMA reads)
