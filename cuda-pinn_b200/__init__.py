@@ -97,6 +97,9 @@ def lib():
     L.pinn_tensor_dot_scratch.argtypes = [sz]; L.pinn_tensor_dot_scratch.restype = sz
     L.pinn_tensor_dot.argtypes = [C.c_int, vp, vp, sz, vp, vp, vp]
     L.pinn_tensor_add_multiple.argtypes = [C.c_int, P(vp), sz, sz, vp, vp]
+    L.pinn_tensor_broadcast.argtypes = [C.c_int, C.c_int, vp, P(sz), C.c_int, vp, P(sz), C.c_int, vp, P(sz), C.c_int, vp]
+    L.pinn_tensor_einsum.argtypes = [C.c_int, C.c_char_p, vp, P(sz), C.c_int, vp, P(sz), C.c_int, vp, vp]
+    L.pinn_tensor_normalize_columns.argtypes = [vp, sz, sz, P(C.c_float), P(C.c_float), P(C.c_float), vp]
     L.pinn_device_alloc.argtypes = [P(vp), sz, vp]
     L.pinn_device_free.argtypes = [vp, vp]
     L.pinn_device_upload.argtypes = [vp, vp, sz, vp]
@@ -467,3 +470,35 @@ def tensor_add_multiple(srcs):
     if rc:
         raise PinnError(rc, "pinn_tensor_add_multiple failed")
     return r
+
+
+def _shape_arr(shape):
+    return (C.c_size_t * max(len(shape), 1))(*shape)
+
+
+def tensor_broadcast(op, a, a_shape, b, b_shape):
+    """NumPy-rule broadcasting (pinn_tensor_broadcast); returns (DeviceArray, result shape)."""
+    r_shape = tuple(np.broadcast_shapes(tuple(a_shape), tuple(b_shape)))
+    r = DeviceArray(n=int(np.prod(r_shape)), dtype=a.dtype)
+    rc = lib().pinn_tensor_broadcast(op, a.code, a.ptr, _shape_arr(a_shape), len(a_shape), b.ptr, _shape_arr(b_shape), len(b_shape),
+                                     r.ptr, _shape_arr(r_shape), len(r_shape), None)
+    if rc:
+        raise PinnError(rc, "pinn_tensor_broadcast failed")
+    return r, r_shape
+
+
+def tensor_einsum(spec, a, a_shape, b, b_shape, out_size):
+    r = DeviceArray(n=max(int(out_size), 1), dtype=a.dtype)
+    rc = lib().pinn_tensor_einsum(a.code, spec.encode(), a.ptr, _shape_arr(a_shape), len(a_shape), b.ptr, _shape_arr(b_shape), len(b_shape), r.ptr, None)
+    return rc, r
+
+
+def tensor_normalize_columns(x, n, d, lo=None, hi=None):
+    """In place; returns the (lo, hi) bounds used."""
+    stats = (C.c_float * (2 * d))()
+    plo = (C.c_float * d)(*lo) if lo is not None else None
+    phi = (C.c_float * d)(*hi) if hi is not None else None
+    rc = lib().pinn_tensor_normalize_columns(x.ptr, n, d, plo, phi, stats, None)
+    if rc:
+        raise PinnError(rc, "pinn_tensor_normalize_columns failed")
+    return np.array(stats[:d], dtype=np.float32), np.array(stats[d:], dtype=np.float32)

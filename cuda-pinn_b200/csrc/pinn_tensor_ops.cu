@@ -6,6 +6,7 @@
 // multiply-add — kernel.cuh:77-80 as nvcc compiles it) — no tensor cores, which would change the rounding.
 // Replaces: include/device/kernel.cuh:10-99 and the host sequences around them in include/tensor.cuh:84-140, 347-508.
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdint>
 #include "../../include/pinn_tensor_abi.h"
 
@@ -168,6 +169,59 @@ __global__ void add_multiple_kernel(const SrcList srcs, int count, size_t n, T* 
     }
 }
 
+// NumPy broadcasting: per-dimension element strides of the operands (0 where the dimension stretches), row-major result
+struct BcastDims { int dim; size_t shape[8]; size_t sa[8]; size_t sb[8]; };
+template <typename T, int OP>
+__global__ void broadcast_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ r, size_t n, const BcastDims bd) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        size_t rem = i, ia = 0, ib = 0;
+        #pragma unroll 1
+        for (int k = bd.dim - 1; k >= 0; k--) {
+            const size_t c = rem % bd.shape[k]; rem /= bd.shape[k];
+            ia += c * bd.sa[k]; ib += c * bd.sb[k];
+        }
+        r[i] = apply<T, OP>(a[ia], b[ib]);
+    }
+}
+
+// per-column minimum / maximum of x[n, d], two fixed-order stages (d <= 8)
+__global__ void __launch_bounds__(256) colminmax_partial(const float* __restrict__ x, size_t n, int d, float* __restrict__ part) {
+    __shared__ float smn[8][8], smx[8][8];
+    float mn[8], mx[8];
+    for (int k = 0; k < 8; k++) { mn[k] = INFINITY; mx[k] = -INFINITY; }
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        for (int k = 0; k < d; k++) { const float v = x[i * d + k]; mn[k] = fminf(mn[k], v); mx[k] = fmaxf(mx[k], v); }
+    for (int k = 0; k < d; k++) {
+        for (int o = 16; o > 0; o >>= 1) { mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o)); mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o)); }
+        if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5][k] = mn[k]; smx[threadIdx.x >> 5][k] = mx[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < d) {
+        float a = INFINITY, b = -INFINITY;
+        for (int w = 0; w < 8; w++) { a = fminf(a, smn[w][threadIdx.x]); b = fmaxf(b, smx[w][threadIdx.x]); }
+        part[(size_t)blockIdx.x * 16 + threadIdx.x] = a; part[(size_t)blockIdx.x * 16 + 8 + threadIdx.x] = b;
+    }
+}
+__global__ void colminmax_final(const float* __restrict__ part, int blocks, int d, float* __restrict__ out) {
+    if (threadIdx.x < d) {
+        float a = INFINITY, b = -INFINITY;
+        for (int i = 0; i < blocks; i++) { a = fminf(a, part[(size_t)i * 16 + threadIdx.x]); b = fmaxf(b, part[(size_t)i * 16 + 8 + threadIdx.x]); }
+        out[threadIdx.x] = a; out[8 + threadIdx.x] = b;
+    }
+}
+struct ColBounds { float lo[8], hi[8]; };
+__global__ void normalize_kernel(float* __restrict__ x, size_t total, int d, const ColBounds cb, const float* __restrict__ dev_bounds) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int k = (int)(i % (size_t)d);
+        const float lo = dev_bounds ? dev_bounds[k] : cb.lo[k], hi = dev_bounds ? dev_bounds[8 + k] : cb.hi[k];
+        // utils::normalize (src/utils.cu): 2.f * (x - lo) / (hi - lo) - 1.f, without contraction into an fma
+        x[i] = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fsub_rn(x[i], lo)), __fsub_rn(hi, lo)), 1.f);
+    }
+}
+
 int grid_for(size_t n, int per_thread) {
     const size_t want = (n + (size_t)256 * per_thread - 1) / ((size_t)256 * per_thread);
     const size_t cap = (size_t)sm_count() * 8;                                  // a multiple of the SM count; grid-stride loops take the rest
@@ -273,6 +327,108 @@ int pinn_tensor_add_multiple(int dtype, const void* const* srcs, size_t count, s
     else if (dtype == 1) add_multiple_kernel<double><<<grid_for(n, 4), 256, 0, st>>>(l, (int)count, n, static_cast<double*>(r));
     else return PINN_ERR_INVALID_ARGUMENT;
     return cudaGetLastError() == cudaSuccess ? PINN_OK : PINN_ERR_CUDA;
+}
+
+int pinn_tensor_broadcast(int op, int dtype, const void* a, const size_t* a_shape, int a_dim, const void* b, const size_t* b_shape, int b_dim,
+                          void* r, const size_t* r_shape, int r_dim, void* stream) {
+    if (!a || !b || !r || !r_shape || r_dim < 1 || r_dim > 8 || a_dim > r_dim || b_dim > r_dim || a_dim < 0 || b_dim < 0 || op < 0 || op > 3 ||
+        (a_dim > 0 && !a_shape) || (b_dim > 0 && !b_shape))
+        return PINN_ERR_INVALID_ARGUMENT;
+    BcastDims bd{};
+    bd.dim = r_dim;
+    size_t n = 1, stra = 1, strb = 1;
+    for (int k = r_dim - 1; k >= 0; k--) {
+        const int ka = k - (r_dim - a_dim), kb = k - (r_dim - b_dim);
+        const size_t da = ka >= 0 ? a_shape[ka] : 1, db = kb >= 0 ? b_shape[kb] : 1, dr = r_shape[k];
+        if (dr == 0 || (da != dr && da != 1) || (db != dr && db != 1) || dr != (da > db ? da : db)) return PINN_ERR_INVALID_ARGUMENT;
+        bd.shape[k] = dr; bd.sa[k] = da == 1 ? 0 : stra; bd.sb[k] = db == 1 ? 0 : strb;
+        stra *= da; strb *= db; n *= dr;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = grid_for(n, 4);
+#define PINN_BCAST(T, OPC) broadcast_kernel<T, OPC><<<grid, 256, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(b), static_cast<T*>(r), n, bd)
+    if (dtype == 0) { switch (op) { case 0: PINN_BCAST(float, 0); break; case 1: PINN_BCAST(float, 1); break; case 2: PINN_BCAST(float, 2); break; default: PINN_BCAST(float, 3); } }
+    else if (dtype == 1) { switch (op) { case 0: PINN_BCAST(double, 0); break; case 1: PINN_BCAST(double, 1); break; case 2: PINN_BCAST(double, 2); break; default: PINN_BCAST(double, 3); } }
+    else return PINN_ERR_INVALID_ARGUMENT;
+#undef PINN_BCAST
+    return cudaGetLastError() == cudaSuccess ? PINN_OK : PINN_ERR_CUDA;
+}
+
+int pinn_tensor_einsum(int dtype, const char* spec, const void* a, const size_t* a_shape, int a_dim, const void* b, const size_t* b_shape, int b_dim,
+                       void* r, void* stream) {
+    if (!spec || !a || !b || !r || !a_shape || !b_shape) return PINN_ERR_INVALID_ARGUMENT;
+    // parse "<A>,<B>-><R>" with 1 or 2 letters per operand and 0..2 for the result
+    char A[3] = {0, 0, 0}, B[3] = {0, 0, 0}, R[3] = {0, 0, 0};
+    int na = 0, nb = 0, nr = 0, part = 0;
+    for (const char* p = spec; *p; p++) {
+        if (*p == ' ') continue;
+        if (*p == ',') { if (part != 0) return PINN_ERR_INVALID_ARGUMENT; part = 1; continue; }
+        if (*p == '-' && p[1] == '>') { if (part != 1) return PINN_ERR_INVALID_ARGUMENT; part = 2; p++; continue; }
+        const bool letter = (*p >= 'a' && *p <= 'z') || (*p >= 'A' && *p <= 'Z');
+        if (!letter) return PINN_ERR_INVALID_ARGUMENT;
+        if (part == 0) { if (na == 2) return PINN_ERR_UNSUPPORTED; A[na++] = *p; }
+        else if (part == 1) { if (nb == 2) return PINN_ERR_UNSUPPORTED; B[nb++] = *p; }
+        else { if (nr == 2) return PINN_ERR_UNSUPPORTED; R[nr++] = *p; }
+    }
+    if (part != 2 || na == 0 || nb == 0 || na != a_dim || nb != b_dim) return PINN_ERR_INVALID_ARGUMENT;
+    auto size_of = [&](char c) -> size_t { for (int i = 0; i < na; i++) if (A[i] == c) return a_shape[i]; for (int i = 0; i < nb; i++) if (B[i] == c) return b_shape[i]; return 0; };
+    for (int i = 0; i < na; i++) for (int k = 0; k < nb; k++) if (A[i] == B[k] && a_shape[i] != b_shape[k]) return PINN_ERR_INVALID_ARGUMENT;
+    if ((na == 2 && A[0] == A[1]) || (nb == 2 && B[0] == B[1])) return PINN_ERR_UNSUPPORTED;
+    if (na == 1 && nb == 1) {
+        if (A[0] == B[0] && nr == 0) return pinn_tensor_dot(dtype, a, b, a_shape[0], r, nullptr, stream);                       // i,i->
+        if (A[0] != B[0] && nr == 2 && R[0] == A[0] && R[1] == B[0]) return pinn_tensor_matmul(dtype, a, 0, b, 0, r, a_shape[0], 1, b_shape[0], stream);   // i,j->ij
+        return PINN_ERR_UNSUPPORTED;
+    }
+    if (na == 2 && nb == 2 && nr == 2) {
+        // the contracted letter: in both operands, not in the result
+        char c = 0;
+        for (int i = 0; i < 2; i++) for (int k = 0; k < 2; k++) if (A[i] == B[k]) c = A[i];
+        if (!c || R[0] == c || R[1] == c) return PINN_ERR_UNSUPPORTED;
+        const char fa = A[0] == c ? A[1] : A[0], fb = B[0] == c ? B[1] : B[0];
+        if (fa == fb || R[0] != fa || R[1] != fb) return PINN_ERR_UNSUPPORTED;
+        return pinn_tensor_matmul(dtype, a, A[0] == c, b, B[1] == c, r, size_of(fa), size_of(c), size_of(fb), stream);
+    }
+    if (na == 2 && nb == 1 && nr == 1) {                                                                                                   // ij,j->i   ji,j->i
+        const char c = B[0];
+        if (A[0] != c && A[1] != c) return PINN_ERR_UNSUPPORTED;
+        const char fa = A[0] == c ? A[1] : A[0];
+        if (R[0] != fa) return PINN_ERR_UNSUPPORTED;
+        return pinn_tensor_matmul(dtype, a, A[0] == c, b, 0, r, size_of(fa), size_of(c), 1, stream);
+    }
+    if (na == 1 && nb == 2 && nr == 1) {                                                                                                   // i,ij->j   i,ji->j
+        const char c = A[0];
+        if (B[0] != c && B[1] != c) return PINN_ERR_UNSUPPORTED;
+        const char fb = B[0] == c ? B[1] : B[0];
+        if (R[0] != fb) return PINN_ERR_UNSUPPORTED;
+        return pinn_tensor_matmul(dtype, a, 0, b, B[1] == c, r, 1, size_of(c), size_of(fb), stream);
+    }
+    return PINN_ERR_UNSUPPORTED;
+}
+
+int pinn_tensor_normalize_columns(float* x, size_t n, size_t d, const float* lo, const float* hi, float* stats_out, void* stream) {
+    if (!x || n == 0 || d == 0 || d > 8 || ((lo == nullptr) != (hi == nullptr))) return PINN_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ColBounds cb{};
+    float* dev_bounds = nullptr;
+    float* part = nullptr;
+    if (lo) {
+        for (size_t k = 0; k < d; k++) { cb.lo[k] = lo[k]; cb.hi[k] = hi[k]; }
+    } else {
+        const int blocks = grid_for(n, 8);
+        if (cudaMallocAsync(&part, (size_t)blocks * 16 * sizeof(float), st) != cudaSuccess || cudaMallocAsync(&dev_bounds, 16 * sizeof(float), st) != cudaSuccess) return PINN_ERR_CUDA;
+        colminmax_partial<<<blocks, 256, 0, st>>>(x, n, (int)d, part);
+        colminmax_final<<<1, 32, 0, st>>>(part, blocks, (int)d, dev_bounds);
+    }
+    normalize_kernel<<<grid_for(n * d, 4), 256, 0, st>>>(x, n * d, (int)d, cb, dev_bounds);
+    int rc = cudaGetLastError() == cudaSuccess ? PINN_OK : PINN_ERR_CUDA;
+    if (dev_bounds) {
+        float h[16];
+        if (cudaMemcpyAsync(h, dev_bounds, sizeof(h), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) rc = PINN_ERR_CUDA;
+        else for (size_t k = 0; k < d; k++) { cb.lo[k] = h[k]; cb.hi[k] = h[8 + k]; }
+        cudaFreeAsync(dev_bounds, st); cudaFreeAsync(part, st);
+    }
+    if (stats_out && rc == PINN_OK) for (size_t k = 0; k < d; k++) { stats_out[k] = cb.lo[k]; stats_out[d + k] = cb.hi[k]; }
+    return rc;
 }
 
 int pinn_device_alloc(void** ptr, size_t bytes, void* stream) {

@@ -55,6 +55,30 @@ int pinn_tensor_dot(int dtype, const void* a, const void* b, size_t n, void* r, 
  * kernel.cuh:55-66).  srcs: HOST array of `count` device pointers (count <= 16), each of n elements. */
 int pinn_tensor_add_multiple(int dtype, const void* const* srcs, size_t count, size_t n, void* r, void* stream);
 
+/* ---- row (f).4: what the reference names but does not define (README.md:54, tensor.cuh:292-313, 467-469) --------------------
+ * The reference gives these no behaviour to be identical to (einsum is an empty stub, broadcast_order is suffix-only, the
+ * normalization of README.md:54 was never written); the semantics here are NumPy's, stated per entry and tested against numpy. */
+
+/* General broadcasting: r = a (op) b with NumPy rules (shapes aligned at the trailing dimension, a dimension of size 1
+ * stretches).  Shapes are HOST arrays; r_shape must be the broadcast of the two (at most 8 dimensions).  Division by zero
+ * follows IEEE (inf / nan): the error channel of pinn_tensor_elementwise belongs to the reference's flat-index semantics. */
+int pinn_tensor_broadcast(int op, int dtype, const void* a, const size_t* a_shape, int a_dim, const void* b, const size_t* b_shape, int b_dim,
+                          void* r, const size_t* r_shape, int r_dim, void* stream);
+
+/* Two-operand einsum for the forms that are ONE contraction over at most one index of vectors / matrices — exactly the products a
+ * dense layer and its backward pass need: "ij,jk->ik" "ji,jk->ik" "ij,kj->ik" "ji,kj->ik" (matmul over transposed views),
+ * "ij,j->i" "i,ij->j" (matrix-vector), "i,i->" (dot), "i,j->ij" (outer product); any index letters.  Shapes as for numpy.einsum;
+ * r has the output's size.  Anything else: PINN_ERR_UNSUPPORTED.  Same kernels and the same per-element order as
+ * pinn_tensor_matmul / pinn_tensor_dot. */
+int pinn_tensor_einsum(int dtype, const char* spec, const void* a, const size_t* a_shape, int a_dim, const void* b, const size_t* b_shape, int b_dim,
+                       void* r, void* stream);
+
+/* Column normalization of a point set x[n, d] in place (README.md:54 "data handling and normalization"): x <- 2 (x - lo) / (hi - lo) - 1
+ * per column, the arithmetic of utils::normalize (src/utils.cu) bit for bit.  lo / hi: HOST arrays of d floats, or both NULL to
+ * use the columns' own minimum / maximum (computed on the device, fixed-order reduction); stats_out (HOST, 2 d floats, may be
+ * NULL) receives the bounds used.  Synchronises when the bounds are computed or returned. */
+int pinn_tensor_normalize_columns(float* x, size_t n, size_t d, const float* lo, const float* hi, float* stats_out, void* stream);
+
 /* Stream-ordered device memory for callers without a CUDA toolchain (ctypes, the tests): cudaMallocAsync / cudaFreeAsync /
  * cudaMemcpyAsync + synchronise.  The reference allocates three buffers per tensor with synchronous cudaMalloc
  * (interface.cuh:86-115). */

@@ -176,6 +176,68 @@ class device_tensor {
             return r;
         }
 
+        // ---- what the reference names but leaves undefined (tensor.cuh:292-313 suffix-only broadcast_order, :467-469 einsum stub):
+        // ---- NumPy semantics, see include/pinn_tensor_abi.h ----
+        // general broadcasting: shapes aligned at the trailing dimension, dimensions of size 1 stretch
+        template<int op>
+        static device_tensor broadcast(const char *opname, const device_tensor &a, const device_tensor &b) {
+            if (!a.data || !b.data)
+                throw std::invalid_argument{std::string{"tensor::"} + opname + ": cannot operate on uninitialized tensors"};
+            const size_t da = a.dim(), db = b.dim(), dr = da > db? da: db;
+            std::vector<size_t> shape_(dr, 1);
+            for (size_t k = 0; k < dr; k++) {
+                const size_t x = k < dr - da? 1: a.shape[k - (dr - da)], y = k < dr - db? 1: b.shape[k - (dr - db)];
+                if (x != y && x != 1 && y != 1) throw std::invalid_argument{std::string{"tensor::"} + opname + ": shapes cannot be broadcast"};
+                shape_[k] = x > y? x: y;
+            }
+            device_tensor r(shape_, a.stream);
+            device_tensor::check(pinn_tensor_broadcast(op, dtype, a.data, a.shape.data(), static_cast<int>(da), b.data, b.shape.data(),
+                                                       static_cast<int>(db), r.data, r.shape.data(), static_cast<int>(dr), a.stream), opname);
+            return r;
+        }
+        static device_tensor broadcast_add(const device_tensor &a, const device_tensor &b) { return device_tensor::broadcast<PINN_OP_ADD>("add", a, b); }
+        static device_tensor broadcast_sub(const device_tensor &a, const device_tensor &b) { return device_tensor::broadcast<PINN_OP_SUB>("sub", a, b); }
+        static device_tensor broadcast_mul(const device_tensor &a, const device_tensor &b) { return device_tensor::broadcast<PINN_OP_MUL>("mul", a, b); }
+        static device_tensor broadcast_div(const device_tensor &a, const device_tensor &b) { return device_tensor::broadcast<PINN_OP_DIV>("div", a, b); }
+
+        // einsum("ij,jk->ik", a, b) and the other single-contraction forms of vectors / matrices (one matmul or dot underneath)
+        static device_tensor einsum(const std::string &spec, const device_tensor &a, const device_tensor &b) {
+            if (!a.data || !b.data) throw std::invalid_argument{"tensor::einsum: cannot contract uninitialized tensors"};
+            if (a.transposed || b.transposed) throw std::invalid_argument{"tensor::einsum: name the transposition in the subscripts instead"};
+            const size_t arrow = spec.find("->");
+            if (arrow == std::string::npos) throw std::invalid_argument{"tensor::einsum: explicit output subscripts required"};
+            std::vector<size_t> shape_;
+            for (size_t q = arrow + 2; q < spec.size(); q++) {
+                if (spec[q] == ' ') continue;
+                size_t extent = 0;
+                size_t pos = 0, ia = 0, ib = 0; bool second = false;
+                for (; pos < arrow; pos++) {
+                    if (spec[pos] == ',') { second = true; continue; }
+                    if (spec[pos] == ' ') continue;
+                    if (spec[pos] == spec[q]) extent = second? (ib < b.shape.size()? b.shape[ib]: 0): (ia < a.shape.size()? a.shape[ia]: 0);
+                    if (second) ib++; else ia++;
+                }
+                if (extent == 0) throw std::invalid_argument{"tensor::einsum: output subscript not found in the operands"};
+                shape_.push_back(extent);
+            }
+            if (shape_.empty()) shape_.push_back(1);
+            device_tensor r(shape_, a.stream);
+            const int status = pinn_tensor_einsum(dtype, spec.c_str(), a.data, a.shape.data(), static_cast<int>(a.dim()), b.data, b.shape.data(),
+                                                  static_cast<int>(b.dim()), r.data, a.stream);
+            if (status == PINN_ERR_UNSUPPORTED) throw std::invalid_argument{"tensor::einsum: only single-contraction forms of vectors and matrices"};
+            device_tensor::check(status, "einsum");
+            return r;
+        }
+
+        // column normalization of a point set [n, d] to [-1, 1] in place (README.md:54); bounds given, or the columns' own min / max
+        device_tensor &normalize(const std::vector<float> &lo = {}, const std::vector<float> &hi = {}) requires std::is_same_v<T, float> {
+            if (this->dim() != 2 || (lo.size() != hi.size()) || (!lo.empty() && lo.size() != this->shape[1]))
+                throw std::invalid_argument{"utils::normalize: expected a [n, d] matrix and d bounds"};
+            device_tensor::check(pinn_tensor_normalize_columns(this->data, this->shape[0], this->shape[1], lo.empty()? nullptr: lo.data(),
+                                                               hi.empty()? nullptr: hi.data(), nullptr, this->stream), "normalize");
+            return *this;
+        }
+
         // metadata only, like the reference's (tensor.cuh:510-592): the copy shares nothing but costs one D2D, the view flag flips
         static device_tensor transpose(const device_tensor &a) {
             if (a.dim() != 2) throw std::invalid_argument{"tensor::transpose: given tensor is not a matrix"};

@@ -65,6 +65,31 @@ int main(void) {
     run<float>("f32_ragged", 130, 37, 65);
     run<float>("f32_layer", 256, 20, 20);
     run<double>("f64_ragged", 67, 129, 33);
+    // row (f).4 through the header: einsum forms = matmul over views, NumPy broadcasting, column normalization
+    {
+        tensor<float> A(as_shape, {9, 5}), B(as_shape, {5, 4}), col(as_shape, {9, 1}), row(as_shape, {1, 4});
+        for (size_t i = 0; i < 45; i++) A[i] = u<float>(11, i);
+        for (size_t i = 0; i < 20; i++) B[i] = u<float>(12, i);
+        for (size_t i = 0; i < 9; i++) col[i] = u<float>(13, i);
+        for (size_t i = 0; i < 4; i++) row[i] = u<float>(14, i);
+        const device_tensor<float> dA(A), dB(B), dcol(col), drow(row);
+        const tensor<float> Z = tensor<float>::matmul(A, B);
+        cout << "f4.einsum_ik=" << mismatches(Z, device_tensor<float>::einsum("ij,jk->ik", dA, dB).to_tensor()) << endl;
+        const tensor<float> G = tensor<float>::matmul(tensor<float>::transpose(A), Z);
+        cout << "f4.einsum_At=" << mismatches(G, device_tensor<float>::einsum("ji,jk->ik", dA, device_tensor<float>(Z)).to_tensor()) << endl;
+        const tensor<float> outer = device_tensor<float>::broadcast_add(dcol, drow).to_tensor();      // (9,1) + (1,4): NOT the reference's flat modulo
+        size_t bad = outer.get_shape() != std::vector<size_t>{9, 4};
+        for (size_t i = 0; i < 9 && !bad; i++) for (size_t k = 0; k < 4; k++) bad += outer.raw()[i * 4 + k] != col.raw()[i] + row.raw()[k];
+        cout << "f4.broadcast_outer=" << bad << endl;
+        tensor<float> pts(as_shape, {6, 2});
+        for (size_t i = 0; i < 12; i++) pts[i] = u<float>(15, i);
+        device_tensor<float> dp(pts); dp.normalize({-1.f, -1.f}, {1.f, 1.f});
+        const tensor<float> back = dp.to_tensor();
+        size_t nb = 0; for (size_t i = 0; i < 12; i++) nb += back.raw()[i] != 2.f * (pts.raw()[i] + 1.f) / 2.f - 1.f;
+        cout << "f4.normalize=" << nb << endl;
+        try { (void)device_tensor<float>::einsum("ijk,kl->ijl", dA, dB); cout << "f4.throws=none" << endl; }
+        catch (const std::invalid_argument &e) { cout << "f4.throws=" << e.what() << endl; }
+    }
     // validation texts and the error channel are the reference's
     const tensor<float> a(as_shape, {2, 3}), b(as_shape, {2, 3});
     try { (void)device_tensor<float>::matmul(device_tensor<float>(a), device_tensor<float>(b)); cout << "throws.matmul=none" << endl; }

@@ -40,7 +40,8 @@ def test_library_exports_the_tensor_abi(P):
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     declared = sorted(set(re.findall(r"\b(pinn_[a-z_0-9]+)\s*\(", src)))
     assert declared == ["pinn_device_alloc", "pinn_device_copy", "pinn_device_download", "pinn_device_free", "pinn_device_upload",
-                        "pinn_tensor_add_multiple", "pinn_tensor_dot", "pinn_tensor_dot_scratch", "pinn_tensor_elementwise", "pinn_tensor_matmul"]
+                        "pinn_tensor_add_multiple", "pinn_tensor_broadcast", "pinn_tensor_dot", "pinn_tensor_dot_scratch", "pinn_tensor_einsum",
+                        "pinn_tensor_elementwise", "pinn_tensor_matmul", "pinn_tensor_normalize_columns"]
     L = P.lib()
     for name in declared:
         assert hasattr(L, name), f"libpinn_b200.so does not export {name}"

@@ -121,5 +121,63 @@ def test_device_tensor_header_equals_the_reference_tensor_in_one_process(oracle)
         for op in ("matmul", "add_bias", "sub", "mul", "div_bias", "mul_small_first", "add3", "matmul_At", "transpose", "inplace_add"):
             assert kv[f"{c}.{op}"] == "0", (c, op, kv[f"{c}.{op}"])
         assert float(kv[f"{c}.dot_rel"]) < 1e-6
+    for k in ("f4.einsum_ik", "f4.einsum_At", "f4.broadcast_outer", "f4.normalize"):
+        assert kv[k] == "0", (k, kv[k])
+    assert kv["f4.throws"].startswith("tensor::einsum:")
     assert kv["throws.matmul"] == "tensor::matmul: invalid shapes"                      # tensor.cuh:354
     assert kv["throws.div"] == "tensor::div: division by zero"                         # runtime.cuh:17-38
+
+
+# ---- row (f).4: NumPy-rule broadcasting, the einsum forms of a dense layer, column normalization (semantics: numpy's; the reference
+# ---- defines none — einsum is an empty stub, tensor.cuh:467-469) -------------------------------------------------------------
+@pytest.mark.parametrize("sa,sb", [((3, 1), (1, 4)), ((5, 4, 3), (3,)), ((2, 1, 6), (7, 1)), ((1,), (4, 5)), ((4, 5), (4, 5)), ((3, 1, 1, 2), (1, 4, 5, 1))])
+def test_general_broadcasting_matches_numpy(P, sa, sb):
+    rng = np.random.default_rng(3)
+    for dt in (np.float32, np.float64):
+        a = rng.standard_normal(sa).astype(dt); b = (rng.standard_normal(sb) + 3).astype(dt)
+        for op, f in ((P.OP_ADD, np.add), (P.OP_SUB, np.subtract), (P.OP_MUL, np.multiply), (P.OP_DIV, np.divide)):
+            R, shape = P.tensor_broadcast(op, P.DeviceArray(a), sa, P.DeviceArray(b), sb)
+            want = f(a, b)
+            assert shape == want.shape and np.array_equal(R.numpy().reshape(shape), want)          # bit-exact: one IEEE operation per element
+
+
+def test_einsum_forms_of_a_dense_layer_match_numpy_and_matmul(P):
+    rng = np.random.default_rng(4)
+    I, K, J = 33, 20, 17
+    a = rng.standard_normal((I, K)).astype(np.float32); b = rng.standard_normal((K, J)).astype(np.float32)
+    v = rng.standard_normal(K).astype(np.float32); u = rng.standard_normal(I).astype(np.float32)
+    A, B, At, Bt, V, U = (P.DeviceArray(x) for x in (a, b, np.ascontiguousarray(a.T), np.ascontiguousarray(b.T), v, u))
+    Z = P.tensor_matmul(A, B, I, K, J).numpy()
+    for spec, x, sx, y, sy in (("ij,jk->ik", A, (I, K), B, (K, J)), ("ji,jk->ik", At, (K, I), B, (K, J)),
+                               ("ij,kj->ik", A, (I, K), Bt, (J, K)), ("ab,cb->ac", A, (I, K), Bt, (J, K)), ("ji,kj->ik", At, (K, I), Bt, (J, K))):
+        rc, R = P.tensor_einsum(spec, x, sx, y, sy, I * J)
+        assert rc == 0 and np.array_equal(R.numpy(), Z), spec                                    # same kernel, same order: bit-identical to matmul
+    rc, R = P.tensor_einsum("ij,j->i", A, (I, K), V, (K,), I)
+    assert rc == 0 and np.allclose(R.numpy(), np.einsum("ij,j->i", a.astype(np.float64), v.astype(np.float64)), rtol=1e-5, atol=1e-5)
+    rc, R = P.tensor_einsum("i,ij->j", U, (I,), A, (I, K), K)
+    assert rc == 0 and np.allclose(R.numpy(), np.einsum("i,ij->j", u.astype(np.float64), a.astype(np.float64)), rtol=1e-5, atol=1e-5)
+    rc, R = P.tensor_einsum("i,i->", V, (K,), V, (K,), 1)
+    assert rc == 0 and R.numpy()[0] == pytest.approx(float(np.dot(v.astype(np.float64), v.astype(np.float64))), rel=1e-6)
+    rc, R = P.tensor_einsum("i,j->ij", U, (I,), V, (K,), I * K)
+    assert rc == 0 and np.array_equal(R.numpy().reshape(I, K), np.outer(u, v))
+    for bad in ("ij,jk->ki", "ii,ij->j", "ijk,kl->ijl", "ij,jk"):
+        rc, _ = P.tensor_einsum(bad, A, (I, K), B, (K, J), I * J)
+        assert rc in (3, 7), bad                                                                 # PINN_ERR_INVALID_ARGUMENT / PINN_ERR_UNSUPPORTED
+    rc, _ = P.tensor_einsum("ij,jk->ik", A, (I, K), A, (I, K), I * K)
+    assert rc == 3                                                                               # contracted sizes differ
+
+
+def test_column_normalization_matches_the_host_helper_arithmetic(P):
+    rng = np.random.default_rng(5)
+    n, d = 100003, 3
+    x = (rng.random((n, d)) * np.array([2.0, 1.0, 6.28]) + np.array([-1.0, 0.0, 0.0])).astype(np.float32)
+    lo = np.array([-1.0, 0.0, 0.0], dtype=np.float32); hi = np.array([1.0, 1.0, 6.28], dtype=np.float32)
+    X = P.DeviceArray(x)
+    P.tensor_normalize_columns(X, n, d, lo, hi)
+    want = (np.float32(2.0) * (x - lo) / (hi - lo) - np.float32(1.0)).astype(np.float32)          # utils::normalize (src/utils.cu), float32 at every step
+    assert np.array_equal(X.numpy().reshape(n, d), want)
+    X = P.DeviceArray(x)
+    glo, ghi = P.tensor_normalize_columns(X, n, d)                                               # bounds from the data itself
+    assert np.array_equal(glo, x.min(axis=0)) and np.array_equal(ghi, x.max(axis=0))
+    y = X.numpy().reshape(n, d)
+    assert y.min() == -1.0 and y.max() == 1.0
