@@ -62,7 +62,7 @@ ABI_SYMBOLS = [
     "pinn_forward", "pinn_residual", "pinn_synchronize",
     "pinn_save", "pinn_load", "pinn_exact_solution", "pinn_evaluate",
     "pinn_comm_unique_id", "pinn_comm_init", "pinn_comm_p2p_export", "pinn_comm_p2p_open", "pinn_step_local", "pinn_step_apply",
-    "pinn_grad_buffer", "pinn_stream", "pinn_profile_enable", "pinn_profile_get",
+    "pinn_grad_buffer", "pinn_stream", "pinn_graph_state", "pinn_profile_enable", "pinn_profile_get",
 ]
 
 _lib = None
@@ -104,6 +104,7 @@ def lib():
     L.pinn_device_free.argtypes = [vp, vp]
     L.pinn_device_upload.argtypes = [vp, vp, sz, vp]
     L.pinn_device_download.argtypes = [vp, vp, sz, vp]
+    L.pinn_graph_state.argtypes = [vp, P(C.c_char_p)]
     L.pinn_create.argtypes = [P(vp), cfgp]
     L.pinn_destroy.argtypes = [vp]; L.pinn_destroy.restype = None
     L.pinn_last_error.argtypes = [vp]; L.pinn_last_error.restype = C.c_char_p
@@ -382,6 +383,12 @@ class Network:
     # -- measurement
     def profile_enable(self, on=True):
         self._check(self._L.pinn_profile_enable(self._h, int(on)))
+
+    def graph_state(self):
+        """(replaying a CUDA graph?, note): the note says why not when capture failed (never silent)."""
+        note = C.c_char_p()
+        st = self._L.pinn_graph_state(self._h, C.byref(note))
+        return st == 1, (note.value or b"").decode()
 
     def profile_get(self, reset=False):
         p = PinnProfile()

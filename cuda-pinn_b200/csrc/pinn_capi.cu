@@ -431,6 +431,7 @@ struct pinn_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;
     uint64_t graph_key[4] = {0, 0, 0, 0}; bool graph_ok = true, capturing = false;
+    std::string graph_note;                            // why the step is not a graph replay (empty: it is, or profiling is on)
     uint64_t step_launches = 0, launches_per_graph = 0;
     float *d_params = nullptr, *d_paramsT = nullptr, *d_m = nullptr, *d_v = nullptr;
     float *d_gbuf = nullptr, *d_partial = nullptr, *d_stash = nullptr, *d_loss = nullptr;
@@ -830,8 +831,8 @@ static int launch_fused(pinn_ctx* c, cudaStream_t stream, bool full, const Point
     const bool timed = c->prof && full && mode == 0 && !c->capturing;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {
-        cudaEventCreate(&e0); cudaEventCreate(&e1);
-        cudaEventRecord(e0, stream);
+        CUDA_TRY(c, "pinn_train_step", cudaEventCreate(&e0)); CUDA_TRY(c, "pinn_train_step", cudaEventCreate(&e1));
+        CUDA_TRY(c, "pinn_train_step", cudaEventRecord(e0, stream));
     }
     if (tc) {
         TcArgs ta{};
@@ -867,7 +868,10 @@ static int launch_mma(pinn_ctx* c, const PointSet& interior, const PointSet* vse
     const int grid = ctas < c->grid_cap_mma ? ctas : c->grid_cap_mma;
     const bool timed = c->prof && !c->capturing;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream); }
+    if (timed) {
+        CUDA_TRY(c, "pinn_train_step", cudaEventCreate(&e0)); CUDA_TRY(c, "pinn_train_step", cudaEventCreate(&e1));
+        CUDA_TRY(c, "pinn_train_step", cudaEventRecord(e0, c->stream));
+    }
     c->kern_mma<<<grid, kMmaWarps * 32, c->mma_smem, c->stream>>>(c->nd, ma);
     if (timed) { cudaEventRecord(e1, c->stream); c->pending.emplace_back(e0, e1); }
     c->last_grid = grid;
@@ -1070,8 +1074,11 @@ static int step_once(pinn_ctx* c) {
             if (e == cudaSuccess && rc == PINN_OK && g) e = cudaGraphInstantiate(&c->graph_exec, g, 0);
             if (e != cudaSuccess || rc != PINN_OK || !c->graph_exec) {
                 if (g) cudaGraphDestroy(g);
+                const cudaError_t why = e != cudaSuccess ? e : cudaGetLastError();
                 cudaGetLastError();
-                c->graph_exec = nullptr; c->graph_ok = false;        // fall back to direct launches for this handle
+                c->graph_exec = nullptr; c->graph_ok = false;        // direct launches for this handle from now on — and say so:
+                c->graph_note = std::string("CUDA graph capture of the step failed (") + (rc != PINN_OK ? c->err : std::string(cudaGetErrorString(why))) +
+                                "): steps are launched kernel by kernel";   // pinn_graph_state() reports it
             } else {
                 c->graph = g; memcpy(c->graph_key, key, sizeof(key));
                 c->launches_per_graph = c->step_launches;
@@ -1778,6 +1785,12 @@ void* pinn_grad_buffer(pinn_ctx* c, size_t* n_floats) {
     return c->d_gbuf;
 }
 void* pinn_stream(pinn_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int pinn_graph_state(const pinn_ctx* c, const char** note) {
+    if (note) *note = c ? c->graph_note.c_str() : "";
+    if (!c) return -1;
+    return c->graph_exec != nullptr ? 1 : 0;
+}
 
 int pinn_profile_enable(pinn_ctx* c, int enable) {
     if (!c) return PINN_ERR_INVALID_ARGUMENT;

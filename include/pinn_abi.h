@@ -320,6 +320,11 @@ typedef struct pinn_profile {
     int32_t  kernel_id;         /* which kernel variant was selected */
 } pinn_profile;
 
+/* 1: the last train step replayed the handle's CUDA graph; 0: steps are launched kernel by kernel (before the first step, while
+ * per-kernel profiling is on, or because capture failed — then *note (valid until the handle is destroyed; may be NULL) says
+ * why instead of the downgrade being silent); -1: null handle. */
+int pinn_graph_state(const pinn_ctx* ctx, const char** note);
+
 /* enable != 0: bracket each fused-kernel launch with CUDA events on the launch stream. */
 int pinn_profile_enable(pinn_ctx* ctx, int enable);
 int pinn_profile_get(pinn_ctx* ctx, pinn_profile* out, int reset);

@@ -196,3 +196,17 @@ def test_training_driver_rejects_bad_arguments():
     assert r.returncode == 1 and "network::baseline: config index must be in 1..5" in r.stderr
     r = subprocess.run([TRAIN, "--config", "1", "--steps", "0", "--resume", "/nonexistent.ckpt"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "pinn_load: cannot open" in r.stderr
+
+
+def test_train_steps_replay_a_cuda_graph_and_say_so(P):
+    """pinn_graph_state: after a step the handle replays its captured graph (C1: mma kernel + fused tail; C5-like net: the cooperative
+    producer / dW-server launch + value launch + tail); with per-kernel profiling on it does not, and the note stays empty (no
+    capture failure to report)."""
+    for which, n in ((1, 4096), (5, 2100)):
+        cfg = P.default_config(which)
+        cfg.n_interior, cfg.n_boundary, cfg.n_initial = n, 300, 300
+        with P.Network(cfg) as net:
+            assert net.graph_state() == (False, "")
+            net.train_step()
+            on, note = net.graph_state()
+            assert on and note == "", (which, on, note)
