@@ -732,11 +732,40 @@ static int configure_kernels(pinn_ctx* c) {
         CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, c->tc_smem));
         if (c->kern_tc_val)
             CUDA_TRY(c, "pinn_create", cudaFuncSetAttribute(c->kern_tc_val, cudaFuncAttributeMaxDynamicSharedMemorySize, c->tc_smem));
+        // CTAs per SM.  cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for the tcgen05 kernels whatever they need (measured on
+        // B200, CUDA 12.9: 128 threads x 128 registers and 40 KB still give 1), which left this kernel at a half or a quarter of its
+        // residency through round 1 and most of round 2 (C3: 72.8 -> 116 Mpts/s with the two CTAs per SM it has room for).  So the
+        // limits are taken from the function and device attributes: registers, shared memory (+ the per-block reservation), threads,
+        // and the TMEM columns each CTA allocates.
         int occ = 0;
-        CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->kern_tc, c->tc_threads, c->tc_smem));
+        {
+            auto fit = [&](pinn_ctx::tc_fn k, int* out) -> int {
+                cudaFuncAttributes fa{};
+                if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(k)) != cudaSuccess) return PINN_ERR_CUDA;
+                int regs_sm = 0, smem_sm = 0, smem_res = 0, thr_sm = 0;
+                cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, c->cfg.device);
+                cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->cfg.device);
+                cudaDeviceGetAttribute(&smem_res, cudaDevAttrReservedSharedMemoryPerBlock, c->cfg.device);
+                cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, c->cfg.device);
+                const int warps = (c->tc_threads + 31) / 32;
+                const int regs_cta = ((fa.numRegs * 32 + 255) / 256 * 256) * warps;          // allocated per warp in units of 256
+                const int smem_cta = c->tc_smem + (int)fa.sharedSizeBytes + smem_res;
+                int o = regs_cta > 0 ? regs_sm / regs_cta : 0;
+                if (smem_cta > 0 && smem_sm / smem_cta < o) o = smem_sm / smem_cta;
+                if (thr_sm / c->tc_threads < o) o = thr_sm / c->tc_threads;
+                *out = o;
+                return PINN_OK;
+            };
+            int o1 = 0, o2 = 1 << 30;
+            if (fit(c->kern_tc, &o1)) return fail(c, PINN_ERR_CUDA, "pinn_create: cudaFuncGetAttributes failed");
+            if (c->kern_tc_val && fit(c->kern_tc_val, &o2)) return fail(c, PINN_ERR_CUDA, "pinn_create: cudaFuncGetAttributes failed");
+            occ = o1 < o2 ? o1 : o2;
+        }
         if (occ < 1) return fail(c, PINN_ERR_UNSUPPORTED, "pinn_create: tensor-core kernel does not fit on an SM");
         const int tmem_limit = 512 / c->tc_tmem_cols;
+        if (getenv("PINN_DEBUG_OCC")) fprintf(stderr, "[pinn] tc kernel: occupancy %d by registers / shared memory (%d threads, %d B), TMEM allows %d\n", occ, c->tc_threads, c->tc_smem, tmem_limit);
         if (occ > tmem_limit) occ = tmem_limit;
+        if (const char* eo = getenv("PINN_TC_OCC")) { const int o = atoi(eo); if (o >= 1 && o <= tmem_limit) occ = o; }
         c->grid_cap_tc = occ * c->num_sms;
         c->kernel_id = 100 + nterms;
         // Training launches of the six-channel nets at width 128 / 256 (BASELINE C4 / C5): producer + dW-server kernel,

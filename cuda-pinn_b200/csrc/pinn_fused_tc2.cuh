@@ -15,8 +15,10 @@
 //   layer OUTPUTS (a, a', a''),
 //        zbar''_i = s abar''_i          zbar'_i = s abar'_i - 4 a a'_i abar''_i
 //        zbar     = s abar - sum_i 2 a a'_i abar'_i - sum_i (2 a a''_i + 2 a'_i^2) abar''_i
-//   so the 64 KB image leaves by ONE cp.async.bulk store per layer (plus s = 1 - a^2 in bf16, whose relative
-//   accuracy bf16(a) cannot give).  12 + 2 bytes per (point, unit, layer) instead of 24 of FP32 (z', z'').
+//   so the stash is a copy of the 64 KB image (plus s = 1 - a^2 in bf16, whose relative accuracy bf16(a) cannot
+//   give): 12 + 2 bytes per (point, unit, layer) instead of 24 of FP32 (z', z'').  Every thread stores its own
+//   16-byte chunks to shared memory (next UMMA operand) AND to global memory (stash / ring); the one-bulk-store-per-
+//   image alternative is kept behind PINN_TC2_BULK=1 and measures slower.
 //
 //   dW SERVER CTAs (blockIdx >= nprod; q per hidden->hidden layer) never see a point: a 256 x 256 FP32 dW_l
 //   is all of TMEM, so the producers cannot hold it next to their own accumulators, and flushing it per tile
