@@ -460,7 +460,7 @@ struct pinn_ctx {
     // producer / dW-server tensor-core kernel (pinn_fused_tc2.cuh): training launches of the interior set, widths 128 / 256
     typedef void (*tc2_fn)(const NetDims, const Tc2Args);
     tc2_fn kern_tc2 = nullptr;
-    int tc2_q = 0, tc2_nprod = 0, tc2_zdepth = 4, tc2_smem = 0, tc2_T = tc2::T, tc2_threads = 0;   // tc2_T: points per producer tile (tc3: 20)
+    int tc2_q = 0, tc2_nprod = 0, tc2_zdepth = 4, tc2_smem = 0, tc2_T = tc2::T, tc2_threads = 0, tc2_grid = 0;   // tc2_grid: CTAs of the launch (num_sms, or twice that at width 128)   // tc2_T: points per producer tile (tc3: 20)
     __nv_bfloat16 *d_wf = nullptr, *d_wb = nullptr;
     uint8_t *d_st_a = nullptr, *d_st_s = nullptr, *d_zring = nullptr;
     unsigned int* d_tc2_flags = nullptr;
@@ -774,11 +774,20 @@ static int configure_kernels(pinn_ctx* c) {
             const char* e2 = getenv("PINN_TC2");
             const bool want = !(e2 && atoi(e2) == 0);
             if (want && nterms == 1 && (H == 128 || H == 256) && nd.d_in == 3 && nd.n2 == 2 && nd.L >= 2) {
-                int q = H == 256 ? 4 : 7;                       // dW servers per hidden->hidden layer (measured best on C5 / C4)
+                // Width 128 (tc2 only): two CTAs per SM — 2 x 107 KB of shared memory, 2 x 256 TMEM columns, 2 x 256 threads x 128 registers —
+                // so that one CTA's UMMAs run under the other's epilogue.  (A plain launch then: the cooperative-launch check uses the
+                // occupancy calculator that answers 1 for tcgen05 kernels.  All CTAs are resident because nothing else runs on the device
+                // while a step does — and every hand-off wait is bounded and reports its site instead of hanging.)
+                const char* e3a = getenv("PINN_TC3");
+                const char* e2c = getenv("PINN_TC2_CTAS");
+                int ctas = (H == 128 && !(e3a && atoi(e3a) != 0)) ? 2 : 1;
+                if (e2c && atoi(e2c) == 1) ctas = 1;
+                const int grid2 = ctas * c->num_sms;
+                int q = H == 256 ? 4 : (ctas == 2 ? 10 : 7);    // dW servers per hidden->hidden layer (measured best on C5 / C4: q = 8..12 -> 92, 97, 101-104, 102, 100 Mpts/s)
                 if (const char* eq = getenv("PINN_TC2_Q")) q = atoi(eq);
                 if (q < 1) q = 1;
-                while (q > 1 && c->num_sms - (nd.L - 1) * q < c->num_sms / 2) q--;
-                const int nprod = c->num_sms - (nd.L - 1) * q;
+                while (q > 1 && grid2 - (nd.L - 1) * q < grid2 / 2) q--;
+                const int nprod = grid2 - (nd.L - 1) * q;
                 const int smem2 = tc2_smem_bytes(H, nd.L);
                 int coop = 0;
                 CUDA_TRY(c, "pinn_create", cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->cfg.device));
@@ -793,7 +802,7 @@ static int configure_kernels(pinn_ctx* c) {
                     CUDA_TRY(c, "pinn_create", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, c->kern_tc2, c->tc2_threads, smem2));
                     if (occ2 < 1) c->kern_tc2 = nullptr;
                     else {
-                        c->tc2_q = q; c->tc2_nprod = nprod; c->tc2_smem = smem2;
+                        c->tc2_q = q; c->tc2_nprod = nprod; c->tc2_smem = smem2; c->tc2_grid = grid2;
                         if (const char* ez = getenv("PINN_TC2_ZD")) c->tc2_zdepth = atoi(ez);
                         if (c->tc2_zdepth < 2) c->tc2_zdepth = 2;
                         c->kernel_id = (tc3on ? 120 : 110) + nterms;
@@ -936,11 +945,15 @@ static int launch_tc2(pinn_ctx* c, const PointSet& interior, int* rows_out) {
     }
     NetDims nd = c->nd;
     void* kargs[] = {&nd, &a};
-    CUDA_TRY(c, "pinn_train_step", cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(c->kern_tc2), dim3(c->num_sms),
-                                                               dim3(c->tc2_threads), kargs, (size_t)c->tc2_smem, c->stream));
+    if (c->tc2_grid == c->num_sms)
+        CUDA_TRY(c, "pinn_train_step", cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(c->kern_tc2), dim3(c->tc2_grid),
+                                                                   dim3(c->tc2_threads), kargs, (size_t)c->tc2_smem, c->stream));
+    else
+        CUDA_TRY(c, "pinn_train_step", cudaLaunchKernel(reinterpret_cast<const void*>(c->kern_tc2), dim3(c->tc2_grid), dim3(c->tc2_threads), kargs,
+                                                        (size_t)c->tc2_smem, c->stream));
     if (timed) { CUDA_TRY(c, "pinn_train_step", cudaEventRecord(e1, c->stream)); c->pending.emplace_back(e0, e1); }
-    c->last_grid = c->num_sms;
-    *rows_out = c->num_sms;
+    c->last_grid = c->tc2_grid;
+    *rows_out = c->tc2_grid;
     c->step_launches++;
     return PINN_OK;
 }
@@ -1246,7 +1259,7 @@ int pinn_create(pinn_ctx** out, const pinn_config* cfg) {
     c->rows_cap_a = c->grid_cap_full > c->grid_cap_tc ? c->grid_cap_full : c->grid_cap_tc;
     if (c->grid_cap_val > c->rows_cap_a) c->rows_cap_a = c->grid_cap_val;      // pinn_forward uses the value kernel on rows A
     if (c->kern_mma && c->grid_cap_mma * kMmaWarps > c->rows_cap_a) c->rows_cap_a = c->grid_cap_mma * kMmaWarps;
-    if (c->kern_tc2 && c->num_sms > c->rows_cap_a) c->rows_cap_a = c->num_sms;
+    if (c->kern_tc2 && c->tc2_grid > c->rows_cap_a) c->rows_cap_a = c->tc2_grid;
     c->rows_cap_b = c->grid_cap_val > c->grid_cap_tc ? c->grid_cap_val : c->grid_cap_tc;
     const size_t nrows = (size_t)c->rows_cap_a + c->rows_cap_b;
     c->stash_per_cta = (long long)nd.L * nd.C * nd.H * c->TP;   // the tensor-core kernel (16-point tiles) needs no more

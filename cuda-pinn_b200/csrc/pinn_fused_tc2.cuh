@@ -206,7 +206,7 @@ inline int tc2_smem_bytes(int H, int L) {
 // =====================================================================================
 template <int HT>
 __device__ __forceinline__ void dw_server(const NetDims& nd, const Tc2Args& ta, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
-                                          uint64_t* fin_bar_p, uint32_t tmem, float* part) {
+                                          uint64_t* fin_bar_p, uint32_t tmem, float* part, uint32_t tmem_cols = 512u) {
     using namespace tc2;
     constexpr int H = HT, MT = H / 128;
     constexpr uint32_t OPB = (uint32_t)H * 256u, CHS = (uint32_t)H * 16u;
@@ -287,11 +287,14 @@ __device__ __forceinline__ void dw_server(const NetDims& nd, const Tc2Args& ta, 
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 512u);
+    if (warp == 0) umma::tmem_dealloc(tmem, tmem_cols);
 }
 
+// Width 128: the kernel needs 107 KB of shared memory, 256 TMEM columns and — capped at 128 registers — half an SM's register file,
+// so TWO CTAs share an SM (launch bounds below) and one's UMMAs run under the other's epilogue: the two-tiles-in-flight overlap that
+// width 256 has no shared memory for, for free.
 template <int DIN, int N2, int HT>
-__global__ void __launch_bounds__(2 * HT, 1)
+__global__ void __launch_bounds__(2 * HT, HT == 128 ? 2 : 1)
 fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     using namespace tc2;
     constexpr int NC = 1 + DIN + N2;
@@ -318,7 +321,9 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     // from a single thread, against 69 of execution
     const bool issuer_warp = __shfl_sync(0xffffffffu, warp, 0) == kIssuer / 32;
 
-    if (warp == 0) umma::tmem_alloc(&tmem_slot, 512u);
+    constexpr uint32_t TMEM_COLS = HT == 128 ? 256u : 512u;      // accumulators: H columns; output layer: 16 more
+    constexpr uint32_t OUTC = HT == 128 ? 128u : 256u;
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, TMEM_COLS);
     if (tid == 0) {
         umma::mbar_init(&wbar[0], 1); umma::mbar_init(&wbar[1], 1);
         umma::mbar_init(&mma_bar, 2); umma::mbar_init(&m0_bar, 2); umma::mbar_init(&out_bar, 1); umma::mbar_init(&fin_bar, 1); umma::mbar_init(&slab_free, 1);
@@ -333,7 +338,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     const int ntiles = ta.set.ntiles, P = ta.nprod;
 
     if ((int)blockIdx.x >= P) {
-        dw_server<HT>(nd, ta, smem, full_bar, empty_bar, &fin_bar, tmem, part);
+        dw_server<HT>(nd, ta, smem, full_bar, empty_bar, &fin_bar, tmem, part, TMEM_COLS);
         return;
     }
 
@@ -664,9 +669,9 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
         if (issuer_warp) {
             umma::tc_fence_after();
             if (umma::elect_one()) {
-                umma::gemm_issue_lean<H / 16>(tmem + OUTCOL, op_addr, 128, CHS, 256, umma::smem_u32(wo16), 128, CHS, 256,
+                umma::gemm_issue_lean<H / 16>(tmem + OUTC, op_addr, 128, CHS, 256, umma::smem_u32(wo16), 128, CHS, 256,
                                               umma::idesc_bf16(128, 16, 1, 1), 0u);
-                umma::gemm_issue_lean<H / 16>(tmem + OUTCOL, umma::smem_u32(lo_img), 128, CHS, 256, umma::smem_u32(wo16), 128, CHS, 256,
+                umma::gemm_issue_lean<H / 16>(tmem + OUTC, umma::smem_u32(lo_img), 128, CHS, 256, umma::smem_u32(wo16), 128, CHS, 256,
                                               umma::idesc_bf16(128, 16, 1, 1), 1u);
                 umma::mma_commit(&out_bar);
             }
@@ -677,7 +682,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
         if (MT == 2 && tid == kLoader) { loader_second(sc); if (sc < nsteps) { umma::mbar_expect_tx(&wbar[0], SLAB); umma::bulk_g2s(Wb0, slab_src(sc, 0), SLAB, &wbar[0]); } }
         if (warp < 4) {                              // lane n = column n of the tile
             uint32_t r[16];
-            tmem_ld16_nowait(tmem + lane_addr + OUTCOL, r);
+            tmem_ld16_nowait(tmem + lane_addr + OUTC, r);
             tmem_wait16(r);
             *reinterpret_cast<float4*>(ys + tid * 4) =
                 make_float4(__uint_as_float(r[0]) + __uint_as_float(r[8]), __uint_as_float(r[1]) + __uint_as_float(r[9]),
@@ -867,7 +872,7 @@ fused_step_tc2(const NetDims nd, const Tc2Args ta) {
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 512u);
+    if (warp == 0) umma::tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // BF16 mirrors of the hidden->hidden weights in the two slab layouts of Tc2Args (wf, wb).
