@@ -783,7 +783,7 @@ static int configure_kernels(pinn_ctx* c) {
                 int ctas = (H == 128 && !(e3a && atoi(e3a) != 0)) ? 2 : 1;
                 if (e2c && atoi(e2c) == 1) ctas = 1;
                 const int grid2 = ctas * c->num_sms;
-                int q = H == 256 ? 4 : (ctas == 2 ? 10 : 7);    // dW servers per hidden->hidden layer (measured best on C5 / C4: q = 8..12 -> 92, 97, 101-104, 102, 100 Mpts/s)
+                int q = H == 256 ? 3 : (ctas == 2 ? 10 : 7);    // dW servers per hidden->hidden layer (measured best; C5 full size, same box: q = 3 -> 30.7, 4 -> 28.7 Mpts/s, 2 saturates the servers: 21.1; C4: q = 8..12 -> 92, 97, 101-104, 102, 100)
                 if (const char* eq = getenv("PINN_TC2_Q")) q = atoi(eq);
                 if (q < 1) q = 1;
                 while (q > 1 && grid2 - (nd.L - 1) * q < grid2 / 2) q--;
