@@ -14,15 +14,18 @@
 //   Taylor forward, the reverse adjoint, bias gradient, dW_1 and dW_{L+1} are thread-local straight out of tcgen05.ld.
 //   ALL of them work on ONE sub-tile at a time (4 + 1 points per thread) and alternate A, B, A, B: each sub-tile's
 //   epilogue gets the whole SM (4 warps per scheduler instead of 2), and while it runs the other sub-tile's UMMAs do.
-// * TWO ISSUER WARPS (one per sub-tile): wait for the sub-tile's "ready" mbarrier (2 H arrivals), issue its UMMA blocks
-//   with a lean path (descriptors stepped by an add, elect.sync), commit to the sub-tile's "done" mbarrier.  A single
-//   thread issues one UMMA per ~69 cycles whatever N is; two threads interleave to ~37 cycles per N = 64 UMMA, which is
-//   what makes 64-column sub-tiles as cheap as one 128-column tile (measured).
+// * FOUR ISSUER WARPS (sub-tile x M-tile): wait for the sub-tile's "ready" mbarrier (one arrival per epilogue warp), issue
+//   their UMMA block with a lean path (descriptors stepped by an add, elect.sync), commit to the sub-tile's "done"
+//   mbarrier.  A single thread issues one UMMA per ~69 cycles whatever N is; two threads interleave to ~37 cycles per
+//   N = 64 UMMA, which is what makes 64-column sub-tiles as cheap as one 128-column tile (measured).
 // * LOADER WARP: weights travel as 32 KB pieces (M-tile x K-half) through a ring; a piece is refilled as soon as both
 //   sub-tiles' UMMAs on it are done (mbarrier of count two).
 // * HELPER WARP: everything that talks to the dW servers — stash / ring back-pressure (done flags) before a sub-tile's
 //   UMMAs may complete, and the release of ready flags (one per sub-tile; the server waits for both halves of an image).
-// Registers: 96 at launch (640 threads), setmaxnreg moves the four single-thread warps' share to the epilogue warps.
+// Registers (width 256): 768 threads, 80 at launch; setmaxnreg gives the epilogue warps 104, the issuer warps 40, the loader /
+// helper warps 24.
+// STATUS: parity-green and bit-reproducible (tests/test_gpu_parity.py, PINN_TC3=1) but NOT the default: 29.6 Mpts/s against 32.4
+// for tc2 on C5 — see DESIGN.md section 5 for what the five variants of this file measured.
 // The output layer runs on the tensor cores from an FP16 image of A_L (11-bit significands, saturating conversion; the
 // hidden layers keep BF16) against W_{L+1} split hi | lo in FP16.
 // The math, the operand / stash / ring images and the dW-server CTAs are those of tc2 (a tile = the pair A|B = one
