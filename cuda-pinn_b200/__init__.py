@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpinn_b200.so")
+LIB_PATH = os.environ.get("PINN_B200_LIB") or os.path.join(_HERE, "libpinn_b200.so")   # (the override is for A/B measurements of two builds on one box)
 
 PDE_BURGERS, PDE_HELMHOLTZ, PDE_ALLEN_CAHN, PDE_NAVIER_STOKES, PDE_HEAT = 0, 1, 2, 3, 4
 SET_INTERIOR, SET_BOUNDARY, SET_INITIAL = 0, 1, 2
