@@ -297,7 +297,13 @@ def test_producer_server_tensor_kernel_against_float64_oracle(P, oracle, pde, wi
             net.set_params(w)
             out = net.loss_grad()
             res.append((out["loss"], net.get_grads()))
-            assert net.profile_get()["kernel_id"] == 111
+            pr = net.profile_get()
+            assert pr["kernel_id"] == 111
+            # one CTA per SM at width 256 (225 KB of shared memory), TWO at width 128 (107 KB, 256 TMEM columns, 128 registers)
+            assert pr["grid"] % (2 if width == 128 else 1) == 0 and pr["block"] == 2 * width
+            if width == 128:
+                import torch
+                assert pr["grid"] == 2 * torch.cuda.get_device_properties(0).multi_processor_count
     # BF16 bars (stated above); the eight-layer width-256 net accumulates one BF16 rounding per layer and channel and
     # measures 1.6e-2 on its largest gradient entries (the round-1 kernel measures 9e-3..1.6e-2 on the same nets): 2e-2 there
     assert abs(res[0][0] / l_ref - 1) < 5e-3
@@ -540,3 +546,20 @@ def test_device_resident_points_train_without_host_to_device_bytes(P, oracle):
         with pytest.raises(P.PinnError) as ei:                  # a host pointer is not a device pointer
             b.set_points_device(0, xf.ctypes.data, len(xf))
         assert ei.value.code == 3
+
+
+def test_round1_tensor_kernel_takes_every_cta_an_sm_has_room_for(P, oracle):
+    """The occupancy calculator answers 1 for tcgen05 kernels; the library takes the limit from the function / device attributes
+    instead.  Width 64: 2 CTAs per SM with two-term operands (80 KB each), 4 with one term (40 KB; the TMEM
+    columns allow 4) — on enough points to fill them."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    ocfg = oracle.baseline_config(3, n_interior=16 * sms * 8, n_boundary=256)
+    for prec, per_sm in ((1, 2), (2, 4)):
+        with P.Network(pcfg(P, ocfg, precision=prec)) as net:
+            net.profile_enable(True)
+            net.train_step()
+            net.synchronize()
+            pr = net.profile_get()
+        assert pr["kernel_id"] == 100 + (2 if prec == 1 else 1)
+        assert pr["grid"] == per_sm * sms, (prec, pr["grid"])
