@@ -119,15 +119,6 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// A contraction over `ksteps` UMMA K-steps (16 bf16 each): both operands advance by a fixed byte step.
-__device__ __forceinline__ void gemm_issue(uint32_t d_tmem, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep,
-                                           uint32_t b_addr, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep,
-                                           uint32_t idesc, int ksteps, uint32_t accumulate_first) {
-    for (int s = 0; s < ksteps; s++)
-        mma_bf16(d_tmem, smem_desc(a_addr + s * a_kstep, a_lbo, a_sbo), smem_desc(b_addr + s * b_kstep, b_lbo, b_sbo), idesc,
-                 (s > 0) ? 1u : accumulate_first);
-}
-
 // ---- lean issue path (tc3) ------------------------------------------------------------------
 // One UMMA per ~16 SASS instructions (descriptor rebuilt from the address, an ELECT loop around every tcgen05.mma because the
 // compiler cannot see that a `tid == k` branch holds one lane) makes a single issuing thread the bottleneck: ~94 cycles per UMMA
@@ -155,6 +146,17 @@ __device__ __forceinline__ void gemm_issue_lean(uint32_t d_tmem, uint32_t a_addr
     for (int s = 0; s < KSTEPS; s++)
         mma_bf16_words(d_tmem, a_lo + (uint32_t)s * (a_kstep >> 4), a_hi, b_lo + (uint32_t)s * (b_kstep >> 4), b_hi, idesc,
                        (s > 0) ? 1u : accumulate_first);
+}
+
+// A contraction over `ksteps` UMMA K-steps (16 bf16 each): both operands advance by a fixed byte step (run-time step count; the
+// descriptor words are built once and stepped by an add, as in gemm_issue_lean).
+__device__ __forceinline__ void gemm_issue(uint32_t d_tmem, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep,
+                                           uint32_t b_addr, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep,
+                                           uint32_t idesc, int ksteps, uint32_t accumulate_first) {
+    uint32_t a_lo = desc_lo(a_addr, a_lbo), b_lo = desc_lo(b_addr, b_lbo);
+    const uint32_t a_hi = desc_hi(a_sbo), b_hi = desc_hi(b_sbo), a_inc = a_kstep >> 4, b_inc = b_kstep >> 4;
+    for (int s = 0; s < ksteps; s++, a_lo += a_inc, b_lo += b_inc)
+        mma_bf16_words(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, (s > 0) ? 1u : accumulate_first);
 }
 
 // byte offset of element (r, f) of an [R x F] bf16 matrix in the chunk-major layout above
