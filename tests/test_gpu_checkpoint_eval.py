@@ -202,7 +202,7 @@ def test_train_steps_replay_a_cuda_graph_and_say_so(P):
     """pinn_graph_state: after a step the handle replays its captured graph (C1: mma kernel + fused tail; C5-like net: the cooperative
     producer / dW-server launch + value launch + tail); with per-kernel profiling on it does not, and the note stays empty (no
     capture failure to report)."""
-    for which, n in ((1, 4096), (5, 2100)):
+    for which, n in ((1, 4096), (4, 2100), (5, 2100)):      # mma kernel | two plain-launched CTAs per SM | cooperative launch
         cfg = P.default_config(which)
         cfg.n_interior, cfg.n_boundary, cfg.n_initial = n, 300, 300
         with P.Network(cfg) as net:
