@@ -28,7 +28,8 @@ def _ref_ops(oracle, I, K, J, seed):
     return {k: np.array(v.split(), dtype=np.float32) for k, v in kv.items() if not k.startswith("shape")}
 
 
-@pytest.mark.parametrize("I,K,J,seed", [(7, 5, 6, 11), (64, 64, 64, 3), (130, 37, 65, 5), (1, 300, 1, 9), (257, 20, 20, 2)])
+@pytest.mark.parametrize("I,K,J,seed", [(7, 5, 6, 11), (64, 64, 64, 3), (130, 37, 65, 5), (1, 300, 1, 9), (257, 20, 20, 2),
+                                          (1, 1, 1, 4), (3, 4096, 2, 6), (129, 1, 65, 8), (512, 256, 256, 1)])
 def test_matmul_add_dot_equal_the_reference_binary(P, oracle, I, K, J, seed):
     ref = _ref_ops(oracle, I, K, J, seed)
     A, B, bias = P.DeviceArray(ref["A"]), P.DeviceArray(ref["B"]), P.DeviceArray(ref["bias"])
@@ -181,3 +182,18 @@ def test_column_normalization_matches_the_host_helper_arithmetic(P):
     assert np.array_equal(glo, x.min(axis=0)) and np.array_equal(ghi, x.max(axis=0))
     y = X.numpy().reshape(n, d)
     assert y.min() == -1.0 and y.max() == 1.0
+
+
+def test_scalar_and_single_element_operands(P):
+    """Edge cases of the reference's flat-index broadcast: a one-element operand on either side (kernel.cuh:16), one-element dot."""
+    a = np.arange(1, 10, dtype=np.float32); one = np.array([4.0], dtype=np.float32)
+    A, O = P.DeviceArray(a), P.DeviceArray(one)
+    rc, R = P.tensor_elementwise(P.OP_ADD, A, O); assert rc == 0 and np.array_equal(R.numpy(), a + 4.0)
+    rc, R = P.tensor_elementwise(P.OP_SUB, O, A); assert rc == 0 and np.array_equal(R.numpy(), 4.0 - a)
+    rc, R = P.tensor_elementwise(P.OP_DIV, A, O); assert rc == 0 and np.array_equal(R.numpy(), a / np.float32(4.0))
+    rc, R = P.tensor_elementwise(P.OP_MUL, O, A)                                     # first operand smaller: only its one element is written
+    want = np.zeros(9, dtype=np.float32); want[0] = 4.0
+    assert rc == 0 and np.array_equal(R.numpy(), want)
+    assert P.tensor_dot(O, O).numpy()[0] == 16.0
+    rc, R = P.tensor_elementwise(P.OP_DIV, A, P.DeviceArray(np.zeros(1, dtype=np.float32)))
+    assert rc == 1 and np.array_equal(R.numpy(), np.zeros(9, dtype=np.float32))      # every denominator zero: nothing written, error reported
