@@ -38,7 +38,8 @@ __global__ void elementwise_same(const T* __restrict__ a, const T* __restrict__ 
     bool zero = false;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
         const Vec x = reinterpret_cast<const Vec*>(a)[i], y = reinterpret_cast<const Vec*>(b)[i];
-        Vec z = reinterpret_cast<Vec*>(r)[i];                                  // (div: a zero denominator leaves the element as it was)
+        Vec z;
+        if (OP == PINN_OP_DIV) z = reinterpret_cast<Vec*>(r)[i];               // (div only: a zero denominator leaves the element as it was)
         #pragma unroll
         for (int k = 0; k < V; k++) {
             if (OP == PINN_OP_DIV && y.v[k] == T(0)) zero = true;
@@ -65,6 +66,39 @@ __global__ void elementwise_bcast(const T* __restrict__ a, size_t na, const T* _
         const T y = b[ib];
         if (OP == PINN_OP_DIV && y == T(0)) zero = true;
         else r[i] = apply<T, OP>(a[ia], y);
+    }
+    if (OP == PINN_OP_DIV && zero) atomicExch(flag, 1);
+}
+
+// the common broadcast — one operand has the result's size, the other is small (a bias): 16-byte accesses on the big one, the small
+// one through the cache.  AFULL: the first operand is the full-size one.
+template <typename T, int OP, bool AFULL>
+__global__ void elementwise_bcast_vec(const T* __restrict__ a, size_t na, const T* __restrict__ b, size_t nb, T* __restrict__ r, size_t bound,
+                                      int* __restrict__ flag) {
+    constexpr int V = 16 / sizeof(T);
+    struct alignas(16) Vec { T v[V]; };
+    const size_t nv = bound / V, stride = (size_t)gridDim.x * blockDim.x;
+    const uint32_t ns = (uint32_t)(AFULL ? nb : na);                            // (small operand: < 2^32 elements, checked by the caller)
+    bool zero = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const Vec big = reinterpret_cast<const Vec*>(AFULL ? a : b)[i];
+        Vec z;
+        if (OP == PINN_OP_DIV) z = reinterpret_cast<Vec*>(r)[i];
+        uint32_t m = (uint32_t)((i * V) % ns);
+        #pragma unroll
+        for (int k = 0; k < V; k++) {
+            const T sm = (AFULL ? b : a)[m];
+            m = m + 1 == ns ? 0 : m + 1;
+            const T x = AFULL ? big.v[k] : sm, y = AFULL ? sm : big.v[k];
+            if (OP == PINN_OP_DIV && y == T(0)) zero = true;
+            else z.v[k] = apply<T, OP>(x, y);
+        }
+        reinterpret_cast<Vec*>(r)[i] = z;
+    }
+    for (size_t i = nv * V + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bound; i += stride) {
+        const T x = a[i % na], y = b[i % nb];
+        if (OP == PINN_OP_DIV && y == T(0)) zero = true;
+        else r[i] = apply<T, OP>(x, y);
     }
     if (OP == PINN_OP_DIV && zero) atomicExch(flag, 1);
 }
@@ -127,9 +161,23 @@ __global__ void __launch_bounds__(256) matmul_tiled(const T* __restrict__ A, con
 template <typename T>
 __global__ void __launch_bounds__(256) dot_partial(const T* __restrict__ a, const T* __restrict__ b, size_t n, T* __restrict__ partial) {
     __shared__ T warp_sum[8];
-    T s = T(0);
+    constexpr int V = 16 / sizeof(T);
+    struct alignas(16) Vec { T v[V]; };
+    T acc[V];
+    #pragma unroll
+    for (int k = 0; k < V; k++) acc[k] = T(0);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) s = fma(a[i], b[i], s);
+    const bool aligned = (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
+    const size_t nv = aligned ? n / V : 0;                                      // 16-byte loads, V independent accumulators per thread
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const Vec x = reinterpret_cast<const Vec*>(a)[i], y = reinterpret_cast<const Vec*>(b)[i];
+        #pragma unroll
+        for (int k = 0; k < V; k++) acc[k] = fma(x.v[k], y.v[k], acc[k]);
+    }
+    for (size_t i = nv * V + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc[0] = fma(a[i], b[i], acc[0]);
+    T s = acc[0];
+    #pragma unroll
+    for (int k = 1; k < V; k++) s += acc[k];                                    // fixed order
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = s;
@@ -238,6 +286,10 @@ int run_elementwise(const T* a, size_t na, const T* b, size_t nb, T* r, size_t n
     const bool aligned = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)r) & 15) == 0;
     if (bound > 0) {
         if (na == nb && na == nr && aligned) elementwise_same<T, OP><<<grid_for(nr, 16 / sizeof(T) * 2), 256, 0, st>>>(a, b, r, nr, flag);
+        else if (na == nr && bound == nr && nb < (1ull << 32) && aligned)
+            elementwise_bcast_vec<T, OP, true><<<grid_for(nr, 16 / sizeof(T) * 2), 256, 0, st>>>(a, na, b, nb, r, bound, flag);
+        else if (nb == nr && bound == nr && na < (1ull << 32) && aligned)
+            elementwise_bcast_vec<T, OP, false><<<grid_for(nr, 16 / sizeof(T) * 2), 256, 0, st>>>(a, na, b, nb, r, bound, flag);
         else elementwise_bcast<T, OP><<<grid_for(bound, 4), 256, 0, st>>>(a, na, b, nb, r, bound, flag);
     }
     if (cudaGetLastError() != cudaSuccess) return PINN_ERR_CUDA;
@@ -305,8 +357,8 @@ int pinn_tensor_matmul(int dtype, const void* a, int a_transposed, const void* b
 }
 
 size_t pinn_tensor_dot_scratch(size_t n) {
-    const size_t want = (n + 256 * 8 - 1) / (256 * 8);
-    const size_t cap = (size_t)sm_count() * 4;
+    const size_t want = (n + 256 * 16 - 1) / (256 * 16);
+    const size_t cap = (size_t)sm_count() * 8;
     return want < 1 ? 1 : (want > cap ? cap : want);
 }
 

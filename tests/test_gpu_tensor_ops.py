@@ -42,7 +42,11 @@ def test_matmul_add_dot_equal_the_reference_binary(P, oracle, I, K, J, seed):
     v = P.DeviceArray(ref["A"])                                                       # the probe's dot operands: v = A flattened, w = u01(seed + 3)
     w = P.DeviceArray(np.array([float(oracle.lib().pinn_oracle_u01(seed + 3, i)) for i in range(I * K)], dtype=np.float32))
     d = P.tensor_dot(v, w).numpy()[0]
-    assert d == pytest.approx(float(ref["dot"][0]), rel=1e-6, abs=1e-5)               # tolerance stated: 1e-6 relative (+1e-5 absolute near zero) (atomics order in the reference)
+    # tolerance stated: 1e-6 of the sum of |terms| (FP32 accumulation in a different order; the reference combines its 256-element
+    # blocks with atomics in arrival order, so its own last bits vary from run to run)
+    wv = np.array([float(oracle.lib().pinn_oracle_u01(seed + 3, i)) for i in range(I * K)], dtype=np.float64)
+    scale = float(np.abs(ref["A"].astype(np.float64) * wv).sum())
+    assert abs(float(d) - float(ref["dot"][0])) <= 1e-6 * scale + 1e-30
     d2 = P.tensor_dot(v, w).numpy()[0]
     assert d == d2                                                                    # ours is bit-reproducible
 
