@@ -103,23 +103,26 @@ __global__ void elementwise_bcast_vec(const T* __restrict__ a, size_t na, const 
     if (OP == PINN_OP_DIV && zero) atomicExch(flag, 1);
 }
 
-// R[I, J] = A[I, K] B[K, J]: 64 x 64 output tile per CTA, 4 x 4 per thread, K in slices of 16 through shared memory.
-// Every output keeps ONE accumulator and takes its products in ascending k with fma — the reference's order.
-template <typename T, bool TA, bool TB>
+// R[I, J] = A[I, K] B[K, J]: (16 Q) x (16 Q) output tile per CTA of 256 threads, Q x Q register tile per thread (Q = 4: 64 x 64, for
+// narrow results and double; Q = 8: 128 x 128 as 2 x 2 blocks of 4 x 4 so that every shared-memory read is a conflict-free 16 bytes),
+// K in slices of 16 through shared memory.  Every output keeps ONE accumulator and takes its products in ascending k with fma —
+// the reference's order, whatever the tiling.
+template <typename T, bool TA, bool TB, int Q>
 __global__ void __launch_bounds__(256) matmul_tiled(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ R, size_t I, size_t K, size_t J) {
-    constexpr int TM = 64, TN = 64, TK = 16;
+    constexpr int TM = 16 * Q, TN = 16 * Q, TK = 16, NB = Q / 4;                  // NB x NB blocks of 4 x 4 per thread, 64 apart
     __shared__ T As[TK][TM + 4];
     __shared__ T Bs[TK][TN + 4];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;                 // tx: 4 columns, ty: 4 rows
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const size_t i0 = (size_t)blockIdx.y * TM, j0 = (size_t)blockIdx.x * TN;
-    T acc[4][4];
+    T acc[Q][Q];
     #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int a = 0; a < Q; a++)
         #pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] = T(0);
+        for (int b = 0; b < Q; b++) acc[a][b] = T(0);
     for (size_t k0 = 0; k0 < K; k0 += TK) {
         const int kmax = (int)((K - k0) < (size_t)TK ? (K - k0) : (size_t)TK);
         // A slice -> As[k][i] (coalesced along the stored-contiguous index)
+        #pragma unroll
         for (int e = threadIdx.x; e < TM * TK; e += 256) {
             int k, i;
             if (TA) { i = e % TM; k = e / TM; } else { k = e % TK; i = e / TK; }
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(256) matmul_tiled(const T* __restrict__ A, con
             if (gi < I && gk < K) v = TA ? A[gk * I + gi] : A[gi * K + gk];
             As[k][i] = v;
         }
+        #pragma unroll
         for (int e = threadIdx.x; e < TN * TK; e += 256) {
             int k, j;
             if (TB) { k = e % TK; j = e / TK; } else { j = e % TN; k = e / TN; }
@@ -138,21 +142,23 @@ __global__ void __launch_bounds__(256) matmul_tiled(const T* __restrict__ A, con
         }
         __syncthreads();
         for (int k = 0; k < kmax; k++) {                                       // (exact bound: no padded products, the sign of a zero sum is the reference's)
-            T a[4], b[4];
+            T a[Q], b[Q];
             #pragma unroll
-            for (int u = 0; u < 4; u++) { a[u] = As[k][ty * 4 + u]; b[u] = Bs[k][tx * 4 + u]; }
-            #pragma unroll
-            for (int u = 0; u < 4; u++)
+            for (int nb = 0; nb < NB; nb++)
                 #pragma unroll
-                for (int v = 0; v < 4; v++) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+                for (int u = 0; u < 4; u++) { a[nb * 4 + u] = As[k][nb * 64 + ty * 4 + u]; b[nb * 4 + u] = Bs[k][nb * 64 + tx * 4 + u]; }
+            #pragma unroll
+            for (int u = 0; u < Q; u++)
+                #pragma unroll
+                for (int v = 0; v < Q; v++) acc[u][v] = fma(a[u], b[v], acc[u][v]);
         }
         __syncthreads();
     }
     #pragma unroll
-    for (int u = 0; u < 4; u++)
+    for (int u = 0; u < Q; u++)
         #pragma unroll
-        for (int v = 0; v < 4; v++) {
-            const size_t gi = i0 + ty * 4 + u, gj = j0 + tx * 4 + v;
+        for (int v = 0; v < Q; v++) {
+            const size_t gi = i0 + (u >> 2) * 64 + ty * 4 + (u & 3), gj = j0 + (v >> 2) * 64 + tx * 4 + (v & 3);
             if (gi < I && gj < J) R[gi * J + gj] = acc[u][v];
         }
 }
@@ -314,14 +320,20 @@ int dispatch_elementwise(int op, const void* a, size_t na, const void* b, size_t
     return PINN_ERR_INVALID_ARGUMENT;
 }
 
+template <typename T, int Q>
+int launch_matmul(const T* a, int ta, const T* b, int tb, T* r, size_t I, size_t K, size_t J, cudaStream_t st) {
+    const dim3 grid((unsigned)((J + 16 * Q - 1) / (16 * Q)), (unsigned)((I + 16 * Q - 1) / (16 * Q)));
+    if (ta && tb) matmul_tiled<T, true, true, Q><<<grid, 256, 0, st>>>(a, b, r, I, K, J);
+    else if (ta) matmul_tiled<T, true, false, Q><<<grid, 256, 0, st>>>(a, b, r, I, K, J);
+    else if (tb) matmul_tiled<T, false, true, Q><<<grid, 256, 0, st>>>(a, b, r, I, K, J);
+    else matmul_tiled<T, false, false, Q><<<grid, 256, 0, st>>>(a, b, r, I, K, J);
+    return cudaGetLastError() == cudaSuccess ? PINN_OK : PINN_ERR_CUDA;
+}
 template <typename T>
 int run_matmul(const T* a, int ta, const T* b, int tb, T* r, size_t I, size_t K, size_t J, cudaStream_t st) {
-    const dim3 grid((unsigned)((J + 63) / 64), (unsigned)((I + 63) / 64));
-    if (ta && tb) matmul_tiled<T, true, true><<<grid, 256, 0, st>>>(a, b, r, I, K, J);
-    else if (ta) matmul_tiled<T, true, false><<<grid, 256, 0, st>>>(a, b, r, I, K, J);
-    else if (tb) matmul_tiled<T, false, true><<<grid, 256, 0, st>>>(a, b, r, I, K, J);
-    else matmul_tiled<T, false, false><<<grid, 256, 0, st>>>(a, b, r, I, K, J);
-    return cudaGetLastError() == cudaSuccess ? PINN_OK : PINN_ERR_CUDA;
+    // 128 x 128 tiles (8 x 8 per thread) for float results wide and tall enough to fill them, 64 x 64 otherwise
+    if (sizeof(T) == 4 && I > 64 && J > 64) return launch_matmul<T, 8>(a, ta, b, tb, r, I, K, J, st);
+    return launch_matmul<T, 4>(a, ta, b, tb, r, I, K, J, st);
 }
 
 template <typename T>
